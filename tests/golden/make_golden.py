@@ -1,0 +1,170 @@
+"""Generate golden vectors by running the UNMODIFIED reference (/root/reference) on CPU fp32.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python tests/golden/make_golden.py
+Writes tests/golden/*.npz.  Weights are NOT stored: they are re-created anywhere from
+`gast_b200.synth` (numpy RandomState keyed on state_dict key names), the .npz holds the
+state_dict key/shape list, the inputs and the reference outputs.
+"""
+import os
+import sys
+import types
+import json
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = '/root/reference'
+
+# torchsummary is imported by the reference (model/gast_net.py:2) but absent from the image
+sys.modules['torchsummary'] = types.SimpleNamespace(summary=None)
+sys.path.insert(0, REF)
+sys.path.insert(1, os.path.join(REPO, 'gast-net-3dposeestimation_b200'))  # only for gast_b200.synth
+
+from model.gast_net import (SpatioTemporalModel, SpatioTemporalModelOptimized1f,   # noqa: E402
+                            GraphAttentionBlock)
+from model.local_attention import LocalGraph, SemCHGraphConv                         # noqa: E402
+from model.global_attention import MultiGlobalGraph, GlobalGraph                     # noqa: E402
+from model.sem_graph_conv import SemGraphConv                                        # noqa: E402
+from common.skeleton import Skeleton                                                 # noqa: E402
+from common.graph_utils import adj_mx_from_skeleton                                  # noqa: E402
+import model.gast_net as _ref_mod                                                    # noqa: E402
+assert _ref_mod.__file__.startswith(REF), _ref_mod.__file__
+from gast_b200 import synth                                                          # noqa: E402
+
+torch.set_grad_enabled(False)
+
+
+def adj_for(J):
+    p = synth.skeleton_parents(J)
+    return adj_mx_from_skeleton(Skeleton(parents=p, joints_left=[], joints_right=[]))
+
+
+def keys_shapes(m):
+    return [[k, list(v.shape)] for k, v in m.state_dict().items()]
+
+
+def save(name, **kw):
+    meta = kw.pop('meta')
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), meta=json.dumps(meta), **kw)
+    print('wrote', name, {k: getattr(v, 'shape', None) for k, v in kw.items()})
+
+
+def model_case(name, J, fw, ch, B, T, strided, causal=False, dense=False, seed=1, xseed=1234, x=None):
+    adj = adj_for(J)
+    if strided:
+        m = SpatioTemporalModelOptimized1f(adj, J, 2, J, fw, causal=causal, dropout=0.05, channels=ch)
+    else:
+        m = SpatioTemporalModel(adj, J, 2, J, fw, causal=causal, dropout=0.05, channels=ch, dense=dense)
+    synth.randomize_module(m, seed)
+    m.eval()
+    if x is None:
+        x = synth.synth_input(B, T, J, 2, xseed)
+    y = m(torch.from_numpy(x)).contiguous().numpy()
+    meta = dict(kind='model', J=J, filter_widths=fw, channels=ch, strided=strided, causal=causal,
+                dense=dense, seed=seed, keys=keys_shapes(m), pad=m.pad, causal_shift=m.causal_shift,
+                receptive_field=m.receptive_field(), total_causal_shift=m.total_causal_shift())
+    save(name, x=x, y=y, meta=meta)
+
+
+def baseball_input():
+    """Config 1 input exactly as reconstruction.py builds it (:105-145,:192-218,:251-253):
+    json -> person 0 -> coco_h36m -> normalize_screen_coordinates -> edge-pad 13 + flipped twin."""
+    from tools.mpii_coco_h36m import coco_h36m
+    from common.camera import normalize_screen_coordinates
+    with open(os.path.join(REF, 'data/keypoints/baseball.json')) as f:
+        info = json.load(f)
+    nfr = info['data'][-1]['frame_index']
+    kp = np.zeros((2, nfr, 17, 2), dtype=np.float32)
+    for fi in info['data']:
+        for idx, sk in enumerate(fi['skeleton']):
+            if len(sk['bbox']) == 0 or idx + 1 > 2:
+                continue
+            kp[idx, fi['frame_index'] - 1] = np.asarray(sk['pose'], dtype=np.float32)
+    kp = kp[0]
+    kp, valid = coco_h36m(kp)
+    kp = normalize_screen_coordinates(kp[..., :2], w=1920, h=1080)[valid]
+    left, right = [4, 5, 6, 11, 12, 13], [1, 2, 3, 14, 15, 16]
+    b2 = np.expand_dims(np.pad(kp, ((13, 13), (0, 0), (0, 0)), 'edge'), axis=0)
+    b2 = np.concatenate((b2, b2), axis=0)          # generators.py:222-233
+    b2[1, :, :, 0] *= -1
+    b2[1, :, left + right] = b2[1, :, right + left]
+    return b2.astype(np.float32)
+
+
+def module_cases():
+    J, C = 17, 32
+    adj = adj_for(J)
+    x = (0.7 * np.random.RandomState(7).standard_normal((3, 5, J, C))).astype(np.float32)
+    xt = torch.from_numpy(x)
+    # GraphAttentionBlock on (B,C,T,N)
+    blk = GraphAttentionBlock(adj, C, C, p_dropout=0.05)
+    synth.randomize_module(blk, 3)
+    blk.eval()
+    save('mod_block_17_32', x=x, y=blk(xt.permute(0, 3, 1, 2).contiguous()).contiguous().numpy(),
+         meta=dict(kind='block', J=J, C=C, seed=3, keys=keys_shapes(blk)))
+    lg = LocalGraph(adj, C, C, 0.05)
+    synth.randomize_module(lg, 4)
+    lg.eval()
+    save('mod_local_17_32', x=x, y=lg(xt).contiguous().numpy(),
+         meta=dict(kind='local', J=J, C=C, seed=4, keys=keys_shapes(lg)))
+    mg = MultiGlobalGraph(adj, C, C // 4, dropout=0.05)
+    synth.randomize_module(mg, 5)
+    mg.eval()
+    save('mod_mglobal_17_32', x=x, y=mg(xt).contiguous().numpy(),
+         meta=dict(kind='mglobal', J=J, C=C, seed=5, keys=keys_shapes(mg)))
+    gg = GlobalGraph(adj, C, C // 4)
+    synth.randomize_module(gg, 6)
+    gg.eval()
+    xg = xt.reshape(-1, J, C).permute(0, 2, 1).contiguous()
+    save('mod_global_17_32', x=xg.numpy(), y=gg(xg).contiguous().numpy(),
+         meta=dict(kind='global', J=J, C=C, seed=6, keys=keys_shapes(gg)))
+    sc = SemCHGraphConv(C, C, lg.gcn_con.adj[0] if lg.gcn_con.adj.dim() == 3 else lg.gcn_con.adj)
+    synth.randomize_module(sc, 7)
+    save('mod_semch_17_32', x=x, y=sc(xt).contiguous().numpy(), mask=(sc.m[0]).numpy(),
+         meta=dict(kind='semch', J=J, C=C, seed=7, keys=keys_shapes(sc)))
+    # the non-channel-wise SemGraphConv of model/sem_graph_conv.py (shared e, bias=True)
+    sg = SemGraphConv(C, C, lg.gcn_con.adj[0], bias=True)
+    synth.randomize_module(sg, 8)
+    save('mod_semgc_17_32', x=x, y=sg(xt).contiguous().numpy(), mask=sg.m.numpy(),
+         meta=dict(kind='semgc', J=J, C=C, seed=8, keys=keys_shapes(sg)))
+    # 19-joint block
+    J2 = 19
+    adj2 = adj_for(J2)
+    x2 = (0.7 * np.random.RandomState(9).standard_normal((2, 3, J2, 16))).astype(np.float32)
+    blk2 = GraphAttentionBlock(adj2, 16, 16, p_dropout=0.05)
+    synth.randomize_module(blk2, 9)
+    blk2.eval()
+    save('mod_block_19_16', x=x2,
+         y=blk2(torch.from_numpy(x2).permute(0, 3, 1, 2).contiguous()).contiguous().numpy(),
+         meta=dict(kind='block', J=J2, C=16, seed=9, keys=keys_shapes(blk2)))
+
+
+def main():
+    torch.manual_seed(0)
+    module_cases()
+    # small-width end-to-end cases (cheap for the numpy oracle and for CPU CI)
+    model_case('model_17_333_c16_full_T31', 17, [3, 3, 3], 16, 3, 31, strided=False)
+    model_case('model_17_333_c16_1f_T27', 17, [3, 3, 3], 16, 3, 27, strided=True)
+    model_case('model_17_333_c16_1f_T81', 17, [3, 3, 3], 16, 2, 81, strided=True)
+    model_case('model_17_333_c16_causal_full_T30', 17, [3, 3, 3], 16, 2, 30, strided=False, causal=True)
+    model_case('model_17_333_c16_causal_1f_T27', 17, [3, 3, 3], 16, 2, 27, strided=True, causal=True)
+    model_case('model_17_333_c16_dense_T27', 17, [3, 3, 3], 16, 2, 28, strided=False, dense=True)
+    model_case('model_15_333_c16_full_T29', 15, [3, 3, 3], 16, 2, 29, strided=False)
+    model_case('model_16_333_c16_full_T27', 16, [3, 3, 3], 16, 2, 27, strided=False)
+    model_case('model_19_333_c16_full_T29', 19, [3, 3, 3], 16, 2, 29, strided=False)
+    model_case('model_17_35_c8_full_T17', 17, [3, 5], 8, 2, 17, strided=False)
+    model_case('model_17_33333_c8_1f_T243', 17, [3, 3, 3, 3, 3], 8, 1, 243, strided=True)
+    # BASELINE.json configs at full width, small batch
+    model_case('cfg2_17_333_c128_full_T27', 17, [3, 3, 3], 128, 4, 27, strided=False)
+    model_case('cfg2_17_333_c128_full_T40', 17, [3, 3, 3], 128, 1, 40, strided=False)
+    model_case('cfg3_17_333_c128_1f_T27', 17, [3, 3, 3], 128, 4, 27, strided=True)
+    model_case('cfg4_17_3333_c64_full_T81', 17, [3, 3, 3, 3], 64, 2, 81, strided=False)
+    model_case('cfg4_17_3333_c64_1f_T81', 17, [3, 3, 3, 3], 64, 2, 81, strided=True)
+    model_case('cfg5_19_333_c128_full_T27', 19, [3, 3, 3], 128, 4, 27, strided=False)
+    model_case('cfg1_baseball_17_333_c128', 17, [3, 3, 3], 128, 2, 303, strided=False, x=baseball_input())
+
+
+if __name__ == '__main__':
+    main()

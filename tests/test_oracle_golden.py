@@ -1,0 +1,98 @@
+"""Pins the numpy oracle (oracle/gast_oracle.py) against golden outputs of the unmodified
+reference (tests/golden/*.npz, produced by tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+from conftest import load_golden, golden_names
+from oracle import gast_oracle as O
+from gast_b200 import synth
+
+TOL = 2e-5  # fp32 vs fp32 on different op orders; the reference's own fp32-vs-fp64 noise is 2e-7
+
+
+def params_from_meta(meta):
+    return synth.synth_state([(k, tuple(s)) for k, s in meta['keys']], meta['seed'])
+
+
+def adj_for(J):
+    return O.adj_from_parents(synth.skeleton_parents(J))
+
+
+SMALL_MODELS = golden_names('model_')
+CFG_MODELS = golden_names('cfg')
+
+
+@pytest.mark.parametrize('name', SMALL_MODELS + CFG_MODELS)
+def test_model_forward(name):
+    g = load_golden(name)
+    m = g['meta']
+    if name.startswith('cfg1') or name.startswith('cfg4_17_3333_c64_full'):
+        pytest.skip('large dilated case: covered on the GPU path; numpy oracle too slow for CPU CI')
+    p = params_from_meta(m)
+    y = O.forward(g['x'], p, adj_for(m['J']), m['filter_widths'], causal=m['causal'],
+                  strided=m['strided'], dense=m['dense'])
+    assert y.shape == g['y'].shape
+    err = np.abs(y - g['y']).max()
+    assert err < TOL, err
+    pad, shift, _ = O.model_geometry(m['filter_widths'], m['causal'], m['strided'], m['dense'])
+    assert pad == m['pad'] and shift == m['causal_shift']
+    assert 1 + 2 * sum(pad) == m['receptive_field']
+
+
+def test_block():
+    for name in ('mod_block_17_32', 'mod_block_19_16'):
+        g = load_golden(name)
+        m = g['meta']
+        p = params_from_meta(m)
+        adj = adj_for(m['J'])
+        y = O.graph_attention_block(g['x'].transpose(0, 3, 1, 2), p, '', O.local_masks(adj))
+        assert np.abs(y - g['y']).max() < TOL
+
+
+def test_local_and_global_modules():
+    g = load_golden('mod_local_17_32')
+    p = params_from_meta(g['meta'])
+    adj = adj_for(17)
+    assert np.abs(O.local_graph(g['x'], p, '', O.local_masks(adj)) - g['y']).max() < TOL
+    g = load_golden('mod_mglobal_17_32')
+    p = params_from_meta(g['meta'])
+    assert np.abs(O.multi_global_graph(g['x'], p, '') - g['y']).max() < TOL
+    g = load_golden('mod_global_17_32')
+    p = params_from_meta(g['meta'])
+    assert np.abs(O.global_graph(g['x'], p, '') - g['y']).max() < TOL
+
+
+def test_semch_and_shared_e_variant():
+    g = load_golden('mod_semch_17_32')
+    p = params_from_meta(g['meta'])
+    sym, con = O.local_masks(adj_for(17))
+    assert (con == g['mask']).all()
+    assert np.abs(O.semch_graph_conv(g['x'], p['W'], p['e'], con) - g['y']).max() < TOL
+    g = load_golden('mod_semgc_17_32')  # model/sem_graph_conv.py: shared e + bias
+    p = params_from_meta(g['meta'])
+    assert (con == g['mask']).all()
+    assert np.abs(O.semch_graph_conv(g['x'], p['W'], p['e'], con, bias=p['bias']) - g['y']).max() < TOL
+
+
+def test_adjacency_and_masks():
+    a = adj_for(17)
+    assert (a > 0).sum() == 49 and np.allclose(a.sum(1), 1)
+    sym, con = O.local_masks(a)
+    assert sym.sum() == 29 and con.sum() == 54
+    a19 = adj_for(19)
+    assert (a19 > 0).sum() == 55
+    s19, c19 = O.local_masks(a19)
+    assert s19.sum() == 33 and c19.sum() == 62
+    with pytest.raises(KeyError):
+        O.local_masks(np.eye(14, dtype=np.float32))
+
+
+def test_full_equals_1f_and_sliding_window():
+    g = load_golden('model_17_333_c16_full_T31')
+    m = g['meta']
+    p = params_from_meta(m)
+    adj = adj_for(17)
+    x = g['x']
+    full = O.forward(x, p, adj, m['filter_widths'])
+    for t in range(full.shape[1]):
+        one = O.forward(x[:, t:t + 27], p, adj, m['filter_widths'], strided=True)
+        assert np.abs(one[:, 0] - full[:, t]).max() < TOL
