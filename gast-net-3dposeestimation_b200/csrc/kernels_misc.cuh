@@ -1,0 +1,194 @@
+// Small kernels of the lifting path: expand stage, collapsed theta/phi row dots, shrink,
+// and the parameter-preparation kernels (BN folding, adjacency softmax, weight packing).
+#pragma once
+#include "gast_common.cuh"
+
+namespace gast {
+
+// ---------------------------------------------------------------------------------------
+// expand stage (gast_net.py:163-164): ReLU(BN(Conv_{(k,1), F->C}(BN_in(x)))) with both BNs
+// folded into We/be.  x: (B,T,J,Fin) ; out: (B*T0*J, C).   One thread = one row x 4 channels.
+// ---------------------------------------------------------------------------------------
+__global__ void expand_kernel(const float* __restrict__ x, const float* __restrict__ We,
+                              const float* __restrict__ be, float* __restrict__ out,
+                              long long rows, int J, int T, int T0, int stride, int taps,
+                              int Fin, int C) {
+  const int cq = C >> 2;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cq) return;
+  long long row = idx / cq;
+  int c = (int)(idx - row * cq) * 4;
+  long long f = row / J;
+  int j = (int)(row - f * J);
+  long long b = f / T0;
+  int t = (int)(f - b * T0);
+  const float* xin = x + ((b * T + (long long)t * stride) * J + j) * Fin;
+  const int KF = taps * Fin;
+  float v[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) v[q] = __ldg(be + c + q);
+  for (int kk = 0; kk < taps; ++kk)
+    for (int i = 0; i < Fin; ++i) {
+      float xv = __ldg(xin + (long long)kk * J * Fin + i);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = fmaf(__ldg(We + (c + q) * KF + kk * Fin + i), xv, v[q]);
+    }
+  *reinterpret_cast<float4*>(out + row * C + c) =
+      make_float4(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f), fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
+}
+
+// ---------------------------------------------------------------------------------------
+// ab[row][q] = X[row,:] . U[q,:] + cab[q],  q < Q (= 2*heads <= 8).   Warp per row.
+// The theta/phi 1x1 convs followed by the concat-project conv (global_attention.py:60-72)
+// collapse to these 2 dot products per head: f[i,j] = a_i + b_j.
+// ---------------------------------------------------------------------------------------
+template <int Q>
+__global__ void rowdot_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ U,
+                              const float* __restrict__ cab, float* __restrict__ ab,
+                              long long rows, int K) {
+  long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = X + row * ldx;
+  float acc[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) acc[q] = 0.f;
+  for (int k = lane * 4; k < K; k += 128) {
+    float4 xv = ldg4(xr + k);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      float4 u = ldg4(U + (long long)q * K + k);
+      acc[q] = fmaf(xv.x, u.x, fmaf(xv.y, u.y, fmaf(xv.z, u.z, fmaf(xv.w, u.w, acc[q]))));
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < Q; ++q) acc[q] = warp_sum(acc[q]);
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < Q; ++q) ab[row * Q + q] = acc[q] + __ldg(cab + q);
+  }
+}
+
+// shrink (gast_net.py:60,99): y[row][o] = X[row,:] . Ws[o,:], o < 3.   Warp per row.
+__global__ void shrink_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ Ws,
+                              float* __restrict__ y, long long rows, int K) {
+  long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = X + row * ldx;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int k = lane * 4; k < K; k += 128) {
+    float4 xv = ldg4(xr + k);
+    float4 w0 = ldg4(Ws + k), w1 = ldg4(Ws + K + k), w2 = ldg4(Ws + 2 * K + k);
+    a0 = fmaf(xv.x, w0.x, fmaf(xv.y, w0.y, fmaf(xv.z, w0.z, fmaf(xv.w, w0.w, a0))));
+    a1 = fmaf(xv.x, w1.x, fmaf(xv.y, w1.y, fmaf(xv.z, w1.z, fmaf(xv.w, w1.w, a1))));
+    a2 = fmaf(xv.x, w2.x, fmaf(xv.y, w2.y, fmaf(xv.z, w2.z, fmaf(xv.w, w2.w, a2))));
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+  if (lane == 0) { y[row * 3 + 0] = a0; y[row * 3 + 1] = a1; y[row * 3 + 2] = a2; }
+}
+
+// ---------------------------------------------------------------------------------------
+// parameter preparation (eval mode)
+// ---------------------------------------------------------------------------------------
+struct BnP {  // eval BatchNorm as y = x*scale + shift ; null weight => identity
+  const float* w; const float* b; const float* rm; const float* rv;
+};
+
+// out[n][kk*Cin + c] = w[n][c][kk] * scale(n);  bias_out[n] = shift(n)
+__global__ void fold_conv_kernel(float* __restrict__ out, float* __restrict__ bias_out,
+                                 const float* __restrict__ w, int N, int Cin, int taps, BnP bn) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)N * Cin * taps;
+  if (idx < total) {
+    int n = (int)(idx / ((long long)Cin * taps));
+    int rem = (int)(idx - (long long)n * Cin * taps);
+    int kk = rem / Cin, c = rem - kk * Cin;
+    float s = bn.w ? bn.w[n] / sqrtf(bn.rv[n] + BN_EPS) : 1.f;
+    out[idx] = w[((long long)n * Cin + c) * taps + kk] * s;
+  }
+  if (idx < N && bias_out) {
+    int n = (int)idx;
+    float s = bn.w ? bn.w[n] / sqrtf(bn.rv[n] + BN_EPS) : 1.f;
+    bias_out[n] = bn.w ? (bn.b[n] - bn.rm[n] * s) : 0.f;
+  }
+}
+
+// coef[z][c] = softmax over the nonzeros z of row i of e[c][.]  (x BN scale);
+// the -9e15 fill of the reference (local_attention.py:40-42) makes masked entries exactly 0.
+__global__ void semch_coef_kernel(float* __restrict__ coef, float* __restrict__ shift,
+                                  const float* __restrict__ e, int e_row_stride, NbrTable nb,
+                                  int nnz, int C, int J, BnP bn, const float* __restrict__ bias) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * J) return;
+  int c = idx / J, i = idx - c * J;
+  const float* er = e + (long long)c * e_row_stride;
+  float s = bn.w ? bn.w[c] / sqrtf(bn.rv[c] + BN_EPS) : 1.f;
+  int z0 = nb.row_ptr[i], z1 = nb.row_ptr[i + 1];
+  float mx = -3.4e38f;
+  for (int z = z0; z < z1; ++z) mx = fmaxf(mx, er[z]);
+  float sum = 0.f;
+  for (int z = z0; z < z1; ++z) sum += expf(er[z] - mx);
+  for (int z = z0; z < z1; ++z) coef[(long long)z * C + c] = expf(er[z] - mx) / sum * s;
+  if (i == 0 && shift) shift[c] = bn.w ? (bn.b[c] - bn.rm[c] * s) : (bias ? bias[c] : 0.f);
+}
+
+// packed[((tile)*128 + w*64 + cc)][k] = W[w][k][tile*64+cc]  (0 beyond Cout)
+__global__ void semch_pack_kernel(float* __restrict__ packed, const float* __restrict__ W,
+                                  int tiles, int Cin, int Cout) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)tiles * 128 * Cin;
+  if (idx >= total) return;
+  int k = (int)(idx % Cin);
+  int n = (int)(idx / Cin);
+  int tile = n >> 7, within = n & 127;
+  int w = within >> 6, cc = within & 63;
+  int c = tile * 64 + cc;
+  packed[idx] = (c < Cout) ? W[((long long)w * Cin + k) * Cout + c] : 0.f;
+}
+
+// U[2h][k] = sum_m wc[m] theta_w[m][k];  U[2h+1][k] = sum_m wc[Ci+m] phi_w[m][k]
+// cab[2h] = sum_m wc[m] theta_b[m];      cab[2h+1] = sum_m wc[Ci+m] phi_b[m]
+__global__ void global_collapse_kernel(float* __restrict__ U, float* __restrict__ cab,
+                                       const float* __restrict__ tw, const float* __restrict__ tb,
+                                       const float* __restrict__ pw, const float* __restrict__ pb,
+                                       const float* __restrict__ wc, int h, int C, int Ci) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < C) {
+    float a = 0.f, b = 0.f;
+    for (int m = 0; m < Ci; ++m) {
+      a = fmaf(wc[m], tw[(long long)m * C + k], a);
+      b = fmaf(wc[Ci + m], pw[(long long)m * C + k], b);
+    }
+    U[(long long)(2 * h) * C + k] = a;
+    U[(long long)(2 * h + 1) * C + k] = b;
+  }
+  if (k == 0) {
+    float a = 0.f, b = 0.f;
+    for (int m = 0; m < Ci; ++m) { a = fmaf(wc[m], tb[m], a); b = fmaf(wc[Ci + m], pb[m], b); }
+    cab[2 * h] = a;
+    cab[2 * h + 1] = b;
+  }
+}
+
+// We[c][kk*Fin+i] = w[c][i][kk] * s_in[i] * s_e[c];  be[c] = s_e[c]*sum w*t_in + t_e[c]
+__global__ void expand_fold_kernel(float* __restrict__ We, float* __restrict__ be,
+                                   const float* __restrict__ w, int C, int Fin, int taps,
+                                   BnP bin, BnP bex) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float se = bex.w[c] / sqrtf(bex.rv[c] + BN_EPS);
+  float te = bex.b[c] - bex.rm[c] * se;
+  float acc = 0.f;
+  for (int kk = 0; kk < taps; ++kk)
+    for (int i = 0; i < Fin; ++i) {
+      float si = bin.w[i] / sqrtf(bin.rv[i] + BN_EPS);
+      float ti = bin.b[i] - bin.rm[i] * si;
+      float wv = w[((long long)c * Fin + i) * taps + kk];
+      We[(long long)c * taps * Fin + kk * Fin + i] = wv * si * se;
+      acc = fmaf(wv, ti, acc);
+    }
+  be[c] = se * acc + te;
+}
+
+}  // namespace gast

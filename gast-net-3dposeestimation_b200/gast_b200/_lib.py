@@ -1,0 +1,78 @@
+"""ctypes binding of csrc/libgast_b200.so (C ABI: include/gast_b200.h).
+
+There is no fallback: if the shared library is missing or fails to load, importing the
+engine raises with the build command.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libgast_b200.so')
+
+GAST_MAX_STAGES = 8
+KIND_MODEL, KIND_BLOCK, KIND_LOCAL, KIND_MGLOBAL, KIND_SEMCH, KIND_GLOBAL_HEAD = range(6)
+
+# every symbol include/gast_b200.h declares
+SYMBOLS = ['gast_create', 'gast_destroy', 'gast_bind', 'gast_prepare', 'gast_out_frames',
+           'gast_receptive_field', 'gast_workspace_bytes', 'gast_forward',
+           'gast_last_launch_count', 'gast_set_gemm_core', 'gast_last_error', 'gast_version']
+
+
+class GastCfg(C.Structure):
+    _fields_ = [
+        ('kind', C.c_int32), ('num_joints', C.c_int32), ('in_features', C.c_int32),
+        ('channels', C.c_int32), ('channels_out', C.c_int32), ('num_stages', C.c_int32),
+        ('filter_widths', C.c_int32 * GAST_MAX_STAGES),
+        ('causal', C.c_int32), ('dense', C.c_int32), ('strided', C.c_int32),
+        ('heads', C.c_int32), ('semch_shared_e', C.c_int32), ('semch_bias', C.c_int32),
+        ('sym_nnz', C.c_int32), ('con_nnz', C.c_int32),
+        ('sym_rows', C.POINTER(C.c_int32)), ('sym_cols', C.POINTER(C.c_int32)),
+        ('con_rows', C.POINTER(C.c_int32)), ('con_cols', C.POINTER(C.c_int32)),
+        ('device', C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Load the library once; raise loudly when it is absent (no CPU / torch fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            'gast_b200: %s not found. Build it with `python __graft_entry__.py build` '
+            '(or gast-net-3dposeestimation_b200/csrc/build.sh). There is no fallback path.' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.gast_create.argtypes = [C.POINTER(vp), C.POINTER(GastCfg)]
+    lib.gast_create.restype = C.c_int
+    lib.gast_destroy.argtypes = [vp]
+    lib.gast_destroy.restype = None
+    lib.gast_bind.argtypes = [vp, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(C.c_int64)]
+    lib.gast_bind.restype = C.c_int
+    lib.gast_prepare.argtypes = [vp, vp]
+    lib.gast_prepare.restype = C.c_int
+    lib.gast_out_frames.argtypes = [vp, C.c_int32, C.c_int32]
+    lib.gast_out_frames.restype = C.c_int32
+    lib.gast_receptive_field.argtypes = [vp]
+    lib.gast_receptive_field.restype = C.c_int32
+    lib.gast_workspace_bytes.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
+    lib.gast_workspace_bytes.restype = C.c_size_t
+    lib.gast_forward.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, C.c_size_t, vp]
+    lib.gast_forward.restype = C.c_int
+    lib.gast_last_launch_count.argtypes = [vp]
+    lib.gast_last_launch_count.restype = C.c_int32
+    lib.gast_set_gemm_core.argtypes = [vp, C.c_int32]
+    lib.gast_set_gemm_core.restype = C.c_int
+    lib.gast_last_error.argtypes = []
+    lib.gast_last_error.restype = C.c_char_p
+    lib.gast_version.argtypes = []
+    lib.gast_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().gast_last_error().decode('utf-8', 'replace')

@@ -1,0 +1,285 @@
+"""Host glue between the drop-in nn.Module shells (model/*.py) and libgast_b200.so.
+
+For each module instance (and device) the engine keeps one C handle.  The handle borrows
+the module's own parameter/buffer storage (`gast_bind`, no copies), so optimiser steps and
+`load_state_dict` are seen; derived constants are refreshed (`gast_prepare`) whenever a
+tensor's (data_ptr, _version) signature changes.  torch provides device memory (outputs and
+a cached workspace from the caching allocator) and the current CUDA stream -- plumbing only.
+
+No fallback: CPU tensors, a missing library or an unsupported mode raise.
+"""
+import ctypes as C
+import torch
+
+from . import _lib as L
+
+_FORCE_CORE = {'core': 0}   # 0 auto, 1 FFMA (A/B checks of the tcgen05 core on the GPU)
+
+
+def set_gemm_core(core):
+    """0 = auto (tcgen05 where the shape allows), 1 = FP32 FFMA core everywhere."""
+    _FORCE_CORE['core'] = int(core)
+
+
+class GastError(RuntimeError):
+    pass
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise GastError('%s: %s' % (what, L.last_error()))
+
+
+def _mask_lists(m):
+    idx = m.nonzero()        # row-major order == order of `e` (local_attention.py:25,41)
+    rows = (C.c_int32 * len(idx))(*[int(i) for i in idx[:, 0]])
+    cols = (C.c_int32 * len(idx))(*[int(i) for i in idx[:, 1]])
+    return rows, cols, len(idx)
+
+
+def _m2d(m):
+    m = m.detach().cpu()
+    return m[0] if m.dim() == 3 else m
+
+
+class _Handle(object):
+    def __init__(self, module, kind, device, cfg_kw, sym=None, con=None):
+        lib = L.load()
+        self.lib = lib
+        self.kind = kind
+        self.device = device
+        cfg = L.GastCfg()
+        cfg.kind = kind
+        cfg.device = device.index if device.index is not None else torch.cuda.current_device()
+        for k, v in cfg_kw.items():
+            if k == 'filter_widths':
+                for i, fw in enumerate(v):
+                    cfg.filter_widths[i] = int(fw)
+                cfg.num_stages = len(v)
+            else:
+                setattr(cfg, k, int(v))
+        keep = []
+        if sym is not None:
+            r, c, n = _mask_lists(_m2d(sym))
+            cfg.sym_rows, cfg.sym_cols, cfg.sym_nnz = r, c, n
+            keep += [r, c]
+        if con is not None:
+            r, c, n = _mask_lists(_m2d(con))
+            cfg.con_rows, cfg.con_cols, cfg.con_nnz = r, c, n
+            keep += [r, c]
+        self.h = C.c_void_p()
+        _check(lib.gast_create(C.byref(self.h), C.byref(cfg)), 'gast_create')
+        self.sig = None
+        self.ws = None
+        self.core = None
+
+    def __del__(self):
+        try:
+            if getattr(self, 'h', None) and self.h.value:
+                self.lib.gast_destroy(self.h)
+                self.h = C.c_void_p()
+        except Exception:
+            pass
+
+    def refresh(self, module, stream):
+        """(re)bind + prepare when any parameter/buffer moved or changed."""
+        items = [(k, v) for k, v in module.state_dict(keep_vars=True).items()]
+        sig = tuple((v.data_ptr(), v._version) for _, v in items)
+        if _FORCE_CORE['core'] != self.core:
+            _check(self.lib.gast_set_gemm_core(self.h, _FORCE_CORE['core']), 'gast_set_gemm_core')
+            self.core = _FORCE_CORE['core']
+        if sig == self.sig:
+            return
+        n = len(items)
+        keys = (C.c_char_p * n)()
+        ptrs = (C.c_void_p * n)()
+        numel = (C.c_int64 * n)()
+        for i, (k, v) in enumerate(items):
+            if not v.is_cuda or v.device != self.device:
+                raise GastError('parameter %r is on %s, expected %s (call .cuda() on the module)'
+                                % (k, v.device, self.device))
+            if v.dtype == torch.float32 and not v.is_contiguous():
+                raise GastError('parameter %r is not contiguous' % k)
+            keys[i] = k.encode()
+            ptrs[i] = v.data_ptr()
+            numel[i] = v.numel()
+        _check(self.lib.gast_bind(self.h, n, keys, ptrs, numel), 'gast_bind')
+        _check(self.lib.gast_prepare(self.h, C.c_void_p(stream)), 'gast_prepare')
+        self.sig = sig
+
+    def forward(self, x, y, B, T, strided_now, stream):
+        need = self.lib.gast_workspace_bytes(self.h, B, T, strided_now)
+        if need == 0:
+            raise GastError('gast_workspace_bytes: %s' % L.last_error())
+        if self.ws is None or self.ws.numel() < need:
+            self.ws = None
+            self.ws = torch.empty(int(need), dtype=torch.uint8, device=self.device)
+        _check(self.lib.gast_forward(self.h, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), B, T,
+                                     strided_now, C.c_void_p(self.ws.data_ptr()), self.ws.numel(),
+                                     C.c_void_p(stream)), 'gast_forward')
+
+    def launches(self):
+        return int(self.lib.gast_last_launch_count(self.h))
+
+
+def _require_cuda(x, what):
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise GastError('%s: input must be a CUDA tensor -- this implementation has no CPU path' % what)
+    if x.dtype != torch.float32:
+        raise GastError('%s: input must be float32 (got %s)' % (what, x.dtype))
+
+
+def _handle_for(module, device, factory):
+    store = module.__dict__.setdefault('_gast_handles', {})
+    key = (device.type, device.index)
+    h = store.get(key)
+    if h is None:
+        h = factory()
+        store[key] = h
+    return h
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _no_train(module, what):
+    if module.training:
+        raise GastError('%s: training-mode forward/backward is not built yet in this round; '
+                        'call .eval() (no silent fallback is provided)' % what)
+
+
+# ------------------------------------------------------------------------------------------
+def run_model(module, x):
+    """SpatioTemporalModelBase.forward (gast_net.py:84-104) on the CUDA library."""
+    _require_cuda(x, 'SpatioTemporalModel.forward')
+    _no_train(module, 'SpatioTemporalModel.forward')
+    dev = x.device
+    blk0 = module.layers_graph_conv[0].local_graph_layer
+
+    def make():
+        return _Handle(module, L.KIND_MODEL, dev, dict(
+            num_joints=module.num_joints_in, in_features=module.in_features,
+            channels=module._gast_channels, filter_widths=list(module.filter_widths),
+            causal=module._gast_causal, dense=module._gast_dense, strided=module._gast_strided, heads=4),
+            sym=blk0.gcn_sym.m, con=blk0.gcn_con.m)
+    h = _handle_for(module, dev, make)
+    x = x.contiguous()
+    B, T = int(x.shape[0]), int(x.shape[1])
+    # A dilated model fed exactly one receptive field computes only what the strided
+    # schedule computes (same arithmetic per output); skip the unused positions.
+    strided_now = 1 if (module._gast_strided or
+                        (T == module.receptive_field() and not module._gast_dense)) else 0
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        h.refresh(module, st)
+        T_out = h.lib.gast_out_frames(h.h, T, strided_now)
+        if T_out <= 0:
+            raise GastError('forward: %s' % L.last_error())
+        y = torch.empty((B, T_out, module.num_joints_in, 3), dtype=torch.float32, device=dev)
+        h.forward(x, y, B, T, strided_now, st)
+    module.__dict__['_gast_last_launches'] = h.launches()
+    return y
+
+
+def run_block(module, x):
+    """GraphAttentionBlock.forward: x (B,C,T,N) -> (B,2C,T,N) (gast_net.py:22-33)."""
+    _require_cuda(x, 'GraphAttentionBlock.forward')
+    _no_train(module, 'GraphAttentionBlock.forward')
+    dev = x.device
+    lg = module.local_graph_layer
+    Bn, Cc, T, N = x.shape
+
+    def make():
+        return _Handle(module, L.KIND_BLOCK, dev, dict(num_joints=N, channels=Cc, heads=4),
+                       sym=lg.gcn_sym.m, con=lg.gcn_con.m)
+    h = _handle_for(module, dev, make)
+    xl = x.permute(0, 2, 3, 1).contiguous()
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        h.refresh(module, st)
+        y = torch.empty((Bn, T, N, 2 * Cc), dtype=torch.float32, device=dev)
+        h.forward(xl, y, Bn * T, 1, 0, st)
+    return y.permute(0, 3, 1, 2)
+
+
+def run_local(module, x):
+    """LocalGraph.forward: (B,T,J,C) -> (B,T,J,C) (local_attention.py:130-151)."""
+    _require_cuda(x, 'LocalGraph.forward')
+    _no_train(module, 'LocalGraph.forward')
+    dev = x.device
+    Bn, T, N, Cc = x.shape
+
+    def make():
+        return _Handle(module, L.KIND_LOCAL, dev, dict(num_joints=N, channels=Cc),
+                       sym=module.gcn_sym.m, con=module.gcn_con.m)
+    h = _handle_for(module, dev, make)
+    xl = x.contiguous()
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        h.refresh(module, st)
+        y = torch.empty((Bn, T, N, Cc), dtype=torch.float32, device=dev)
+        h.forward(xl, y, Bn * T, 1, 0, st)
+    return y
+
+
+def run_semch(module, x):
+    """SemCHGraphConv.forward / SemGraphConv.forward: (B,T,J,Cin) -> (B,T,J,Cout)."""
+    _require_cuda(x, 'SemCHGraphConv.forward')
+    dev = x.device
+    Bn, T, N, Cc = x.shape
+    shared = 1 if module.e.shape[0] == 1 and module.out_features != 1 else 0
+
+    def make():
+        return _Handle(module, L.KIND_SEMCH, dev, dict(
+            num_joints=N, channels=Cc, channels_out=module.out_features, semch_shared_e=shared,
+            semch_bias=1 if module.bias is not None else 0), sym=module.m)
+    h = _handle_for(module, dev, make)
+    xl = x.contiguous()
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        h.refresh(module, st)
+        y = torch.empty((Bn, T, N, module.out_features), dtype=torch.float32, device=dev)
+        h.forward(xl, y, Bn * T, 1, 0, st)
+    return y
+
+
+def run_multi_global(module, x):
+    """MultiGlobalGraph.forward: (B,T,J,C) -> (B,T,J,C) (global_attention.py:103-130)."""
+    _require_cuda(x, 'MultiGlobalGraph.forward')
+    _no_train(module, 'MultiGlobalGraph.forward')
+    dev = x.device
+    Bn, T, N, Cc = x.shape
+
+    def make():
+        return _Handle(module, L.KIND_MGLOBAL, dev, dict(num_joints=N, channels=Cc,
+                                                         heads=module.num_non_local))
+    h = _handle_for(module, dev, make)
+    xl = x.contiguous()
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        h.refresh(module, st)
+        y = torch.empty((Bn, T, N, Cc), dtype=torch.float32, device=dev)
+        h.forward(xl, y, Bn * T, 1, 0, st)
+    return y
+
+
+def run_global_head(module, x):
+    """GlobalGraph.forward: (B*T, C, N) -> (B*T, Cg, N) (global_attention.py:52-82)."""
+    _require_cuda(x, 'GlobalGraph.forward')
+    dev = x.device
+    BT, Cc, N = x.shape
+    if module.g_channels != module.inter_channels:
+        raise GastError('GlobalGraph with inter_channels == in_channels//2 is not on the lifting path')
+
+    def make():
+        return _Handle(module, L.KIND_GLOBAL_HEAD, dev, dict(num_joints=N, channels=Cc,
+                                                             channels_out=module.inter_channels, heads=1))
+    h = _handle_for(module, dev, make)
+    xl = x.permute(0, 2, 1).contiguous()
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        h.refresh(module, st)
+        y = torch.empty((BT, N, module.g_channels), dtype=torch.float32, device=dev)
+        h.forward(xl, y, BT, 1, 0, st)
+    return y.permute(0, 2, 1)

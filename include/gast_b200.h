@@ -1,0 +1,115 @@
+/*
+ * gast_b200.h -- C ABI of the B200-native GAST-Net 2D->3D lifting path (libgast_b200.so).
+ *
+ * The reference (fabro66/GAST-Net-3DPoseEstimation) is pure Python and has no FFI for this
+ * path; its "plugin boundary" is the Python class API of model/gast_net.py.  This header is
+ * the C boundary underneath our drop-in classes: plain pointers and sizes, no torch types.
+ * Each entry point cites the reference interface it stands in for.
+ *
+ * Ownership: the caller owns ALL device memory that crosses this boundary (parameters,
+ * buffers, gradients, inputs, outputs, workspace).  A handle owns only small derived
+ * constants (folded/packed weights) that gast_prepare() recomputes.  Nothing here
+ * synchronises the device or allocates on the forward path; all work is enqueued on the
+ * caller's stream.  Every call returns 0 on success, non-zero on error with a message in
+ * gast_last_error() (thread-local).  Nothing throws or aborts.
+ */
+#ifndef GAST_B200_H
+#define GAST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gast_handle gast_t;
+
+/* What a handle computes.  MODEL is the product; the others are the reference's
+ * sub-modules, exposed so that parity can be tested module by module. */
+enum gast_kind {
+  GAST_KIND_MODEL = 0,       /* SpatioTemporalModel / ...Optimized1f   model/gast_net.py:107,180 */
+  GAST_KIND_BLOCK = 1,       /* GraphAttentionBlock                    model/gast_net.py:8-33    */
+  GAST_KIND_LOCAL = 2,       /* LocalGraph                             model/local_attention.py:59-151 */
+  GAST_KIND_MGLOBAL = 3,     /* MultiGlobalGraph                       model/global_attention.py:85-130 */
+  GAST_KIND_SEMCH = 4,       /* SemCHGraphConv / SemGraphConv          model/local_attention.py:10-56, model/sem_graph_conv.py:10-55 */
+  GAST_KIND_GLOBAL_HEAD = 5  /* GlobalGraph                            model/global_attention.py:7-82 */
+};
+
+#define GAST_MAX_STAGES 8
+
+/* Mirrors the constructor arguments of SpatioTemporalModel(adj, num_joints_in, in_features,
+ * num_joints_out, filter_widths, causal, dropout, channels, dense) (model/gast_net.py:113-114)
+ * and SpatioTemporalModelOptimized1f(...) (:191-192).  The adjacency enters as the two
+ * LocalGraph masks (model/local_attention.py:92-114) in row-major nonzero order, which is the
+ * order the learnable `e` is scattered in (:25,:41). */
+typedef struct gast_cfg {
+  int32_t kind;                          /* enum gast_kind */
+  int32_t num_joints;                    /* J: 15, 16, 17 or 19 */
+  int32_t in_features;                   /* 2 (MODEL only) */
+  int32_t channels;                      /* MODEL: `channels`; other kinds: input width C */
+  int32_t channels_out;                  /* SEMCH: out_features; GLOBAL_HEAD: inter_channels; else 0 */
+  int32_t num_stages;                    /* len(filter_widths) (MODEL only) */
+  int32_t filter_widths[GAST_MAX_STAGES];
+  int32_t causal;
+  int32_t dense;                         /* SpatioTemporalModel(dense=True) ablation */
+  int32_t strided;                       /* 1 = Optimized1f schedule, 0 = dilated */
+  int32_t heads;                         /* MGLOBAL/GLOBAL_HEAD: number of heads (BLOCK/MODEL: 4) */
+  int32_t semch_shared_e;                /* SEMCH: 1 = one `e` row shared by all channels (sem_graph_conv.py) */
+  int32_t semch_bias;                    /* SEMCH: 1 = has bias */
+  int32_t sym_nnz, con_nnz;              /* nonzeros of the two masks (SEMCH uses `sym` only) */
+  const int32_t* sym_rows; const int32_t* sym_cols;   /* host arrays, row-major nonzero order */
+  const int32_t* con_rows; const int32_t* con_cols;
+  int32_t device;                        /* CUDA device ordinal */
+} gast_cfg;
+
+/* nn.Module construction (gast_net.py:113-157).  Copies cfg (incl. the mask arrays). */
+int gast_create(gast_t** out, const gast_cfg* cfg);
+void gast_destroy(gast_t* h);
+
+/* Borrow the caller's parameter / buffer storage by state_dict key (SURVEY.md 8b lists the
+ * keys; they are exactly `module.state_dict().keys()` of the reference classes).  Pointers
+ * are device pointers to contiguous fp32 (int64 for num_batches_tracked, ignored).  No copy:
+ * optimiser updates are seen after the next gast_prepare().  Stands in for
+ * nn.Module.load_state_dict / .parameters() (main.py:193,207-208). */
+int gast_bind(gast_t* h, int32_t n, const char* const* keys, void* const* dev_ptrs,
+              const int64_t* numel);
+
+/* Recompute the eval-mode derived constants from the bound parameters: BN folded into the
+ * adjacent conv, softmaxed per-channel adjacencies, packed SemCH weights, collapsed
+ * theta/phi vectors.  Call after binding and after every parameter change (the Python shim
+ * tracks tensor versions).  Enqueued on `stream` (a cudaStream_t). */
+int gast_prepare(gast_t* h, void* stream);
+
+/* Output frames for an input of T frames: T - rf + 1 (dilated) or the strided count
+ * (gast_net.py:62-69,159-177,236-251).  `strided_now` = schedule actually used. Returns <0 on error. */
+int32_t gast_out_frames(const gast_t* h, int32_t T, int32_t strided_now);
+int32_t gast_receptive_field(const gast_t* h);
+
+/* Bytes of caller-provided scratch gast_forward needs for a (B,T) batch. */
+size_t gast_workspace_bytes(const gast_t* h, int32_t B, int32_t T, int32_t strided_now);
+
+/* forward(x) (gast_net.py:84-104), eval mode.
+ *   MODEL:  x (B,T,J,in_features) fp32 -> y (B,T_out,J,3) fp32, both contiguous.
+ *           strided_now: 0 = dilated schedule (any T >= rf), 1 = strided schedule
+ *           (T a multiple of the receptive field pattern, as Optimized1f requires).
+ *   other kinds: x is (B frames, J, C) with T == 1; y is (B, J, C_out)
+ *           (BLOCK: C_out = 2C, channels-last).
+ * All work is enqueued on `stream`. */
+int gast_forward(gast_t* h, const float* x, float* y, int32_t B, int32_t T,
+                 int32_t strided_now, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernels the last gast_forward enqueued (for bench.py's gpu_launches). */
+int32_t gast_last_launch_count(const gast_t* h);
+
+/* GEMM core selection for A/B checks on the GPU: 0 = auto (tcgen05 where the shape
+ * allows), 1 = force the FP32 FFMA core.  Not a fallback switch: both are CUDA paths. */
+int gast_set_gemm_core(gast_t* h, int32_t core);
+
+const char* gast_last_error(void);
+const char* gast_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAST_B200_H */

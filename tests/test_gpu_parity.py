@@ -1,0 +1,196 @@
+"""GPU parity: the CUDA path (through the C ABI, via the drop-in modules) against
+(i) golden outputs of the unmodified reference and (ii) the numpy oracle on seeded inputs.
+Tolerance: 1e-4 absolute per coordinate in fp32 (BASELINE.json north_star); the FFMA core
+is held to 2e-5."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, golden_names
+from gast_b200 import synth, engine
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+TOL_FFMA = 2e-5
+
+
+def _adj(J):
+    from common.skeleton import Skeleton
+    from common.graph_utils import adj_mx_from_skeleton
+    return adj_mx_from_skeleton(Skeleton(synth.skeleton_parents(J), [], []))
+
+
+def build_model(meta, device='cuda'):
+    from model.gast_net import SpatioTemporalModel, SpatioTemporalModelOptimized1f
+    J = meta['J']
+    if meta['strided']:
+        m = SpatioTemporalModelOptimized1f(_adj(J), J, 2, J, meta['filter_widths'], causal=meta['causal'],
+                                           dropout=0.05, channels=meta['channels'])
+    else:
+        m = SpatioTemporalModel(_adj(J), J, 2, J, meta['filter_widths'], causal=meta['causal'],
+                                dropout=0.05, channels=meta['channels'], dense=meta['dense'])
+    assert [[k, list(v.shape)] for k, v in m.state_dict().items()] == meta['keys']
+    synth.randomize_module(m, meta['seed'])
+    return m.to(device).eval()
+
+
+@pytest.fixture(params=[0, 1], ids=['auto', 'ffma'])
+def core(request):
+    engine.set_gemm_core(request.param)
+    yield request.param
+    engine.set_gemm_core(0)
+
+
+@pytest.mark.parametrize('name', golden_names('model_') + golden_names('cfg'))
+def test_model_vs_reference_golden(name, core):
+    g = load_golden(name)
+    m = build_model(g['meta'])
+    with torch.no_grad():
+        y = m(torch.from_numpy(g['x']).cuda())
+    assert tuple(y.shape) == g['y'].shape
+    err = np.abs(y.cpu().numpy() - g['y']).max()
+    assert err < (TOL_FFMA if core == 1 else TOL), err
+    assert m.receptive_field() == g['meta']['receptive_field']
+    assert m.total_causal_shift() == g['meta']['total_causal_shift']
+    assert m.pad == g['meta']['pad'] and m.causal_shift == g['meta']['causal_shift']
+
+
+def test_modules_vs_reference_golden(core):
+    from model.gast_net import GraphAttentionBlock
+    from model.local_attention import LocalGraph, SemCHGraphConv, local_adjacencies
+    from model.global_attention import MultiGlobalGraph, GlobalGraph
+    from model.sem_graph_conv import SemGraphConv
+    tol = TOL_FFMA if core == 1 else TOL
+    for name in ('mod_block_17_32', 'mod_block_19_16'):
+        g = load_golden(name)
+        J, Cc = g['meta']['J'], g['meta']['C']
+        blk = GraphAttentionBlock(_adj(J), Cc, Cc, 0.05)
+        synth.randomize_module(blk, g['meta']['seed'])
+        blk = blk.cuda().eval()
+        y = blk(torch.from_numpy(g['x']).cuda().permute(0, 3, 1, 2))
+        assert np.abs(y.cpu().numpy() - g['y']).max() < tol
+    g = load_golden('mod_local_17_32')
+    lg = LocalGraph(_adj(17), 32, 32, 0.05)
+    synth.randomize_module(lg, g['meta']['seed'])
+    y = lg.cuda().eval()(torch.from_numpy(g['x']).cuda())
+    assert np.abs(y.cpu().numpy() - g['y']).max() < tol
+    g = load_golden('mod_mglobal_17_32')
+    mg = MultiGlobalGraph(_adj(17), 32, 8, dropout=0.05)
+    synth.randomize_module(mg, g['meta']['seed'])
+    y = mg.cuda().eval()(torch.from_numpy(g['x']).cuda())
+    assert np.abs(y.cpu().numpy() - g['y']).max() < tol
+    g = load_golden('mod_global_17_32')
+    gg = GlobalGraph(_adj(17), 32, 8)
+    synth.randomize_module(gg, g['meta']['seed'])
+    y = gg.cuda().eval()(torch.from_numpy(g['x']).cuda())
+    assert np.abs(y.cpu().numpy() - g['y']).max() < tol
+    _, con = local_adjacencies(_adj(17))
+    g = load_golden('mod_semch_17_32')
+    sc = SemCHGraphConv(32, 32, con)
+    synth.randomize_module(sc, g['meta']['seed'])
+    y = sc.cuda()(torch.from_numpy(g['x']).cuda())
+    assert np.abs(y.cpu().numpy() - g['y']).max() < tol
+    g = load_golden('mod_semgc_17_32')
+    sg = SemGraphConv(32, 32, con, bias=True)
+    synth.randomize_module(sg, g['meta']['seed'])
+    y = sg.cuda()(torch.from_numpy(g['x']).cuda())
+    assert np.abs(y.cpu().numpy() - g['y']).max() < tol
+
+
+def test_against_oracle_random_shapes(core):
+    """seeded inputs at sizes the numpy oracle finishes in seconds; odd batch / ragged tiles."""
+    from oracle import gast_oracle as O
+    tol = TOL_FFMA if core == 1 else TOL
+    for (J, fw, ch, B, T, strided, causal) in [
+            (17, [3, 3, 3], 32, 5, 27, True, False),
+            (17, [3, 3, 3], 32, 1, 33, False, False),
+            (19, [3, 3], 32, 3, 11, False, True),
+            (15, [3, 3, 3], 16, 2, 27, True, True),
+            (17, [3, 3, 3], 64, 9, 27, False, False)]:
+        meta = dict(J=J, filter_widths=fw, channels=ch, strided=strided, causal=causal, dense=False, seed=11)
+        from model.gast_net import SpatioTemporalModel, SpatioTemporalModelOptimized1f
+        cls = SpatioTemporalModelOptimized1f if strided else SpatioTemporalModel
+        m = cls(_adj(J), J, 2, J, fw, causal=causal, dropout=0.05, channels=ch)
+        synth.randomize_module(m, 11)
+        p = {k: v.numpy() for k, v in m.state_dict().items()}
+        x = synth.synth_input(B, T, J, 2, seed=99 + B)
+        ref = O.forward(x, p, O.adj_from_parents(synth.skeleton_parents(J)), fw, causal=causal, strided=strided)
+        with torch.no_grad():
+            y = m.cuda().eval()(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert y.shape == ref.shape
+        assert np.abs(y - ref).max() < tol, (J, fw, ch, B, T, np.abs(y - ref).max())
+
+
+def test_full_size_properties():
+    """BASELINE config 2 at full size (4096 clips): size-independent properties.
+    (a) batch independence: a clip's output does not depend on its batch neighbours (bit-exact);
+    (b) full model == Optimized1f on the same weights (state_dict interchangeable);
+    (c) sliding window: T=40 sequence == 14 independent 27-frame clips;
+    (d) MPJPE equal to 3 decimals (mm) between (b)'s two paths."""
+    g = load_golden('cfg2_17_333_c128_full_T27')
+    m = build_model(g['meta'])
+    B = 4096
+    x = torch.from_numpy(synth.synth_input(B, 27, 17, 2, seed=1234)).cuda()
+    with torch.no_grad():
+        y = m(x)
+        y_head = m(x[:100].contiguous())
+        assert torch.equal(y[:100], y_head)
+        y_tail = m(x[B - 37:].contiguous())
+        assert torch.equal(y[B - 37:], y_tail)
+        meta1 = dict(g['meta'], strided=True)
+        m1 = build_model(meta1)
+        m1.load_state_dict(m.state_dict())
+        y1 = m1(x)
+        assert (y - y1).abs().max().item() < 1e-5
+        # the first 4 clips of this seed are the golden's input
+        assert np.abs(y[:4].cpu().numpy() - g['y']).max() < TOL
+        xs = torch.from_numpy(synth.synth_input(3, 40, 17, 2, seed=5)).cuda()
+        ys = m(xs)
+        assert ys.shape == (3, 14, 17, 3)
+        wins = torch.stack([xs[:, t:t + 27] for t in range(14)], 1).reshape(3 * 14, 27, 17, 2).contiguous()
+        yw = m(wins).reshape(3, 14, 17, 3)
+        assert (ys - yw).abs().max().item() < 2e-5
+    gt = torch.from_numpy(synth.synth_target(B, 17)).cuda()
+    mp = lambda a: (torch.norm(a - gt, dim=3).mean().item() * 1000.0)
+    assert round(mp(y), 3) == round(mp(y1), 3)
+
+
+def test_error_behaviour():
+    from model.gast_net import SpatioTemporalModel
+    from model.local_attention import LocalGraph
+    m = SpatioTemporalModel(_adj(17), 17, 2, 17, [3, 3, 3], channels=16).cuda().eval()
+    with pytest.raises(AssertionError):
+        m(torch.zeros(2, 27, 16, 2, device='cuda'))      # gast_net.py:94
+    with pytest.raises(AssertionError):
+        m(torch.zeros(2, 27, 17, 3, device='cuda'))      # gast_net.py:95
+    with pytest.raises(AssertionError):
+        m(torch.zeros(27, 17, 2, device='cuda'))         # gast_net.py:93
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 20, 17, 2, device='cuda'))      # shorter than the receptive field
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 27, 17, 2))                     # CPU tensor: no fallback
+    with pytest.raises(KeyError):
+        LocalGraph(torch.eye(14), 16, 16)                # local_attention.py:89-90
+    with pytest.raises(AssertionError):
+        SpatioTemporalModel(_adj(17), 17, 2, 17, [3, 4, 3], channels=16)   # gast_net.py:46-47
+
+
+def test_state_dict_roundtrip_and_inplace_output():
+    """load_state_dict after the first forward must be seen (main.py:252), and callers write
+    into the returned tensor in place (reconstruction.py:165-166)."""
+    g = load_golden('model_17_333_c16_full_T31')
+    m = build_model(g['meta'])
+    x = torch.from_numpy(g['x']).cuda()
+    with torch.no_grad():
+        y0 = m(x).clone()
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        synth.randomize_module(m, 77)
+        y1 = m(x)
+        assert (y1 - y0).abs().max().item() > 1e-3
+        m.load_state_dict(sd)
+        y2 = m(x)
+        assert torch.equal(y2, y0)
+        y2[1, :, :, 0] *= -1
+        y2[1, :, [4, 5, 6, 1, 2, 3]] = y2[1, :, [1, 2, 3, 4, 5, 6]]
+        assert torch.mean(y2, dim=0, keepdim=True).shape == (1, 5, 17, 3)
