@@ -82,9 +82,35 @@ struct gast_handle {
   float *We = nullptr, *be = nullptr;
   bool prepared = false;
   int launches = 0;
+  int tc_launches = 0;
   int gemm_core = 0;                 // 0 auto (tcgen05 where possible), 1 force FFMA
+  // optional per-launch device timing (bench.py roofline): event pairs around every launch
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_kind;          // kind per recorded launch
+  size_t ev_used = 0;
   int fpt = 0;
   int sm_count = 148;
+};
+
+enum { LK_EXPAND = 0, LK_GEMM_PLAIN = 1, LK_GEMM_SEMCH = 2, LK_GEMM_GLOBAL = 3, LK_ROWDOT = 4, LK_SHRINK = 5,
+       LK_TC_PLAIN = 6, LK_TC_SEMCH = 7, LK_TC_GLOBAL = 8 };
+
+struct TimedLaunch {   // RAII: event pair around one launch when timing is on
+  gast_handle* h; cudaStream_t st; bool on;
+  TimedLaunch(gast_handle* h_, cudaStream_t st_, int kind) : h(h_), st(st_), on(h_->timing) {
+    if (!on) return;
+    while (h->ev_pool.size() < h->ev_used + 2) {
+      cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e);
+    }
+    h->ev_kind.push_back(kind);
+    cudaEventRecord(h->ev_pool[h->ev_used], st);
+  }
+  ~TimedLaunch() {
+    if (!on) return;
+    cudaEventRecord(h->ev_pool[h->ev_used + 1], st);
+    h->ev_used += 2;
+  }
 };
 
 static int dalloc(gast_handle* h, float** p, size_t nfloats) {
@@ -233,6 +259,7 @@ extern "C" int gast_create(gast_t** out, const gast_cfg* cfg) {
 extern "C" void gast_destroy(gast_t* h) {
   if (!h) return;
   for (void* p : h->owned) cudaFree(p);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   delete h;
 }
 
@@ -251,6 +278,27 @@ extern "C" int gast_set_gemm_core(gast_t* h, int32_t core) {
 }
 
 extern "C" int32_t gast_last_launch_count(const gast_t* h) { return h ? h->launches : -1; }
+extern "C" int32_t gast_last_tc_launch_count(const gast_t* h) { return h ? h->tc_launches : -1; }
+
+extern "C" int gast_set_timing(gast_t* h, int32_t on) {
+  if (!h) return fail("null handle");
+  h->timing = on != 0;
+  return 0;
+}
+
+extern "C" int32_t gast_get_timings(gast_t* h, int32_t max_n, float* ms, int32_t* kinds) {
+  if (!h) return -1;
+  int n = (int)(h->ev_used / 2);
+  if (n > max_n) n = max_n;
+  for (int i = 0; i < n; ++i) {
+    if (cudaEventSynchronize(h->ev_pool[2 * i + 1]) != cudaSuccess) return -1;
+    float t = 0.f;
+    cudaEventElapsedTime(&t, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]);
+    ms[i] = t;
+    kinds[i] = h->ev_kind[i];
+  }
+  return n;
+}
 
 // ------------------------------------------------------------------------------------------
 // prepare
@@ -509,12 +557,15 @@ static int launch_gemm(gast_handle* h, cudaStream_t st, int epi, const GemmP& p,
   for (int s = 0; s < p.nseg; ++s) Ktot += p.seg[s].K;
   if (Ktot != p.ldw) return fail("internal: K mismatch %d vs %d", Ktot, p.ldw);
   if (p.N % 4 || p.ld_out % 4) return fail("internal: N/ld_out must be multiples of 4");
-  if (h->gemm_core == 0 && tcw && tc_supported(p, epi)) {
+  if (h->gemm_core == 0 && tcw && tc_supported(p, epi, *tcw)) {
+    TimedLaunch tl(h, st, LK_TC_PLAIN + epi);
     int rc = tc_launch(h->sm_count, st, epi, p, *tcw);
     if (rc) return fail("tcgen05 gemm launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     h->launches++;
+    h->tc_launches++;
     return 0;
   }
+  TimedLaunch tl(h, st, LK_GEMM_PLAIN + epi);
   dim3 grid(cdiv(p.F, p.fpt), cdiv(p.N, FF_BN));
   int hpt = 1;
   if (epi == EPI_GLOBAL) hpt = p.heads < 4 ? p.heads : 4;
@@ -539,6 +590,7 @@ static int launch_rowdot(gast_handle* h, cudaStream_t st, const float* X, int ld
   if (rows <= 0) return 0;
   const int Q = 2 * b.heads;
   unsigned blocks = cdiv(rows * 32, 256);
+  TimedLaunch tl(h, st, LK_ROWDOT);
   if (Q == 8) rowdot_kernel<8><<<blocks, 256, 0, st>>>(X, ldx, b.U, b.cab, ab, rows, b.C);
   else if (Q == 6) rowdot_kernel<6><<<blocks, 256, 0, st>>>(X, ldx, b.U, b.cab, ab, rows, b.C);
   else if (Q == 4) rowdot_kernel<4><<<blocks, 256, 0, st>>>(X, ldx, b.U, b.cab, ab, rows, b.C);
@@ -656,6 +708,9 @@ extern "C" int gast_forward(gast_t* h, const float* x, float* y, int32_t B, int3
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUDA_OK(cudaSetDevice(h->cfg.device));
   h->launches = 0;
+  h->tc_launches = 0;
+  h->ev_used = 0;
+  h->ev_kind.clear();
   const size_t need = gast_workspace_bytes(h, B, T, strided_now);
   if (need == 0) return 1;
   if (workspace_bytes < need || !workspace)
@@ -688,6 +743,7 @@ extern "C" int gast_forward(gast_t* h, const float* x, float* y, int32_t B, int3
   {
     long long rows = F * J;
     long long thr = rows * (C / 4);
+    TimedLaunch tl(h, st, LK_EXPAND);
     expand_kernel<<<cdiv(thr, 256), 256, 0, st>>>(x, h->We, h->be, mb.act[0], rows, J, T, g.T0, g.s0,
                                                  c.filter_widths[0], c.in_features, C);
     h->launches++;
@@ -731,6 +787,7 @@ extern "C" int gast_forward(gast_t* h, const float* x, float* y, int32_t B, int3
     const float* ws = Lk.get("shrink.weight", (int64_t)3 * Cl);
     if (!Lk.ok) return 1;
     long long rows = F * J;
+    TimedLaunch tl(h, st, LK_SHRINK);
     shrink_kernel<<<cdiv(rows * 32, 256), 256, 0, st>>>(mb.act[cur], Cl, ws, y, rows, Cl);
     h->launches++;
   }

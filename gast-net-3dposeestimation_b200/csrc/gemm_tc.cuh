@@ -3,6 +3,6 @@
 #include "gast_common.cuh"
 namespace gast {
 struct TcWeights { float* hi = nullptr; float* lo = nullptr; };
-inline bool tc_supported(const GemmP&, int) { return false; }
+inline bool tc_supported(const GemmP&, int, const TcWeights&) { return false; }
 inline int tc_launch(int, cudaStream_t, int, const GemmP&, const TcWeights&) { return (int)cudaErrorNotSupported; }
 }  // namespace gast

@@ -15,7 +15,8 @@ KIND_MODEL, KIND_BLOCK, KIND_LOCAL, KIND_MGLOBAL, KIND_SEMCH, KIND_GLOBAL_HEAD =
 # every symbol include/gast_b200.h declares
 SYMBOLS = ['gast_create', 'gast_destroy', 'gast_bind', 'gast_prepare', 'gast_out_frames',
            'gast_receptive_field', 'gast_workspace_bytes', 'gast_forward',
-           'gast_last_launch_count', 'gast_set_gemm_core', 'gast_last_error', 'gast_version']
+           'gast_last_launch_count', 'gast_last_tc_launch_count', 'gast_set_timing',
+           'gast_get_timings', 'gast_set_gemm_core', 'gast_last_error', 'gast_version']
 
 
 class GastCfg(C.Structure):
@@ -64,6 +65,12 @@ def load():
     lib.gast_forward.restype = C.c_int
     lib.gast_last_launch_count.argtypes = [vp]
     lib.gast_last_launch_count.restype = C.c_int32
+    lib.gast_last_tc_launch_count.argtypes = [vp]
+    lib.gast_last_tc_launch_count.restype = C.c_int32
+    lib.gast_set_timing.argtypes = [vp, C.c_int32]
+    lib.gast_set_timing.restype = C.c_int
+    lib.gast_get_timings.argtypes = [vp, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    lib.gast_get_timings.restype = C.c_int32
     lib.gast_set_gemm_core.argtypes = [vp, C.c_int32]
     lib.gast_set_gemm_core.restype = C.c_int
     lib.gast_last_error.argtypes = []

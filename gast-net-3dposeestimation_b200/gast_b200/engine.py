@@ -283,3 +283,49 @@ def run_global_head(module, x):
         y = torch.empty((BT, N, module.g_channels), dtype=torch.float32, device=dev)
         h.forward(xl, y, BT, 1, 0, st)
     return y.permute(0, 2, 1)
+
+
+LAUNCH_KINDS = ['expand', 'gemm_ffma_plain', 'gemm_ffma_semch', 'gemm_ffma_global', 'rowdot', 'shrink',
+                'gemm_tc_plain', 'gemm_tc_semch', 'gemm_tc_global']
+
+
+def profile_forward(module, x, reps=5):
+    """Per-launch device times of the model forward (CUDA events inside the library, on the
+    launching stream).  Returns per-kernel-kind ms per step and the GEMM-family totals."""
+    dev = x.device
+    with torch.no_grad():
+        run_model(module, x)
+    h = module.__dict__['_gast_handles'][(dev.type, dev.index)]
+    lib = h.lib
+    _check(lib.gast_set_timing(h.h, 1), 'gast_set_timing')
+    acc = {}
+    n_launch = {}
+    try:
+        for _ in range(reps):
+            with torch.no_grad():
+                run_model(module, x)
+            ms = (C.c_float * 512)()
+            kinds = (C.c_int32 * 512)()
+            n = lib.gast_get_timings(h.h, 512, ms, kinds)
+            if n < 0:
+                raise GastError('gast_get_timings failed')
+            n_launch = {}
+            for i in range(n):
+                k = LAUNCH_KINDS[kinds[i]]
+                acc[k] = acc.get(k, 0.0) + ms[i]
+                n_launch[k] = n_launch.get(k, 0) + 1
+    finally:
+        lib.gast_set_timing(h.h, 0)
+    per = {k: v / reps for k, v in acc.items()}
+    gemm = sum(v for k, v in per.items() if k.startswith('gemm'))
+    ng = sum(v for k, v in n_launch.items() if k.startswith('gemm'))
+    tc = int(lib.gast_last_tc_launch_count(h.h))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        e0.record()
+        run_model(module, x)
+        e1.record()
+    torch.cuda.synchronize(dev)
+    return {'per_kernel_ms': per, 'launches': n_launch, 'gemm_ms_per_step': gemm, 'gemm_launches': ng,
+            'step_ms': e0.elapsed_time(e1), 'workspace_bytes': int(h.ws.numel()) if h.ws is not None else 0,
+            'gemm_core': ('tcgen05-3xtf32 x%d + ffma x%d' % (tc, ng - tc)) if tc else 'ffma-fp32'}

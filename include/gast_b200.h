@@ -102,6 +102,17 @@ int gast_forward(gast_t* h, const float* x, float* y, int32_t B, int32_t T,
 /* Number of kernels the last gast_forward enqueued (for bench.py's gpu_launches). */
 int32_t gast_last_launch_count(const gast_t* h);
 
+/* Number of those that ran on the tcgen05 (tensor-core) GEMM core. */
+int32_t gast_last_tc_launch_count(const gast_t* h);
+
+/* Per-launch device timing for the roofline report: when on, gast_forward brackets every
+ * kernel launch with a CUDA event pair on the caller's stream; gast_get_timings waits for
+ * them and returns up to max_n (milliseconds, kind) pairs of the last forward.  kinds:
+ * 0 expand, 1-3 FFMA GEMM (plain/SemCH/global epilogue), 4 theta/phi row-dot, 5 shrink,
+ * 6-8 tcgen05 GEMM (plain/SemCH/global). */
+int gast_set_timing(gast_t* h, int32_t on);
+int32_t gast_get_timings(gast_t* h, int32_t max_n, float* ms, int32_t* kinds);
+
 /* GEMM core selection for A/B checks on the GPU: 0 = auto (tcgen05 where the shape
  * allows), 1 = force the FP32 FFMA core.  Not a fallback switch: both are CUDA paths. */
 int gast_set_gemm_core(gast_t* h, int32_t core);
