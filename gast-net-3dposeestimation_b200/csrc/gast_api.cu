@@ -798,7 +798,70 @@ extern "C" int gast_forward(gast_t* h, const float* x, float* y, int32_t B, int3
 // ------------------------------------------------------------------------------------------
 // tcgen05 weight copies
 // ------------------------------------------------------------------------------------------
+static int prep_one_tc(gast_handle* h, cudaStream_t st, TcWeights& t, const float* W, int N, int K) {
+  if (!W) return 0;
+  int rc = tc_prepare_weights(t, W, N, K, st, &h->owned);
+  if (rc) return fail("tcgen05 weight preparation failed (%d): %s", rc,
+                      rc > 0 ? cudaGetErrorString((cudaError_t)rc) : "cuTensorMapEncodeTiled unavailable/failed");
+  return 0;
+}
+
 static int prepare_tc(gast_handle* h, cudaStream_t st) {
-  (void)h; (void)st;
+  const int kind = h->cfg.kind;
+  for (BlockConsts& b : h->blocks) {
+    const int C = b.C;
+    const int nmask = (kind == GAST_KIND_SEMCH) ? 1 : 2;
+    if (prep_one_tc(h, st, b.tc_loc, b.Wloc, nmask * b.tpm * 128, C)) return 1;
+    if (prep_one_tc(h, st, b.tc_lc, b.Wlc, C, 2 * C)) return 1;
+    if (prep_one_tc(h, st, b.tc_g, b.Wg, b.heads * b.Cg, C)) return 1;
+    if (prep_one_tc(h, st, b.tc_gc, b.Wgc, C, C)) return 1;
+    if (prep_one_tc(h, st, b.tc_bc, b.Wbc, 2 * C, 3 * C)) return 1;
+  }
+  for (StageConsts& s : h->stages) {
+    if (prep_one_tc(h, st, s.tc_t, s.Wt, s.Cw, s.taps * s.Cw)) return 1;
+    if (prep_one_tc(h, st, s.tc_1, s.W1, s.Cw, s.Cw)) return 1;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// debug / probe entry: out[M,N] = A[M,K] . W[N,K]^T on a chosen GEMM core (test infrastructure
+// for the numerics of the tensor-core path; not used by the forward).
+// ------------------------------------------------------------------------------------------
+extern "C" int gast_debug_gemm(const float* A, const float* W, float* out, int32_t M, int32_t N, int32_t K,
+                               int32_t core, int32_t tc_mode, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (M <= 0 || N <= 0 || K <= 0 || N % 4 || K % 4) return fail("gast_debug_gemm: bad shape");
+  GemmP p;
+  memset(&p, 0, sizeof(p));
+  p.F = M; p.J = 1; p.fpt = 128;
+  p.res_map = RowMap{1, 1, 1, 0};
+  p.nseg = 1;
+  p.seg[0].base = A; p.seg[0].ld = K; p.seg[0].K = K; p.seg[0].Kc = K; p.seg[0].tap_stride = 0;
+  p.seg[0].map = RowMap{1, 1, 1, 0};
+  p.W = W; p.ldw = K; p.N = N; p.out = out; p.ld_out = N;
+  p.tc_mode = tc_mode;
+  if (core == 0) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    TcWeights t;
+    std::vector<void*> owned;
+    int rc = tc_prepare_weights(t, W, N, K, st, &owned);
+    if (rc || !t.ready || !tc_supported(p, EPI_PLAIN, t)) {
+      for (void* q : owned) cudaFree(q);
+      return fail("gast_debug_gemm: shape not supported by the tcgen05 core (rc=%d)", rc);
+    }
+    rc = tc_launch(sms, st, EPI_PLAIN, p, t);
+    cudaError_t e = cudaStreamSynchronize(st);
+    for (void* q : owned) cudaFree(q);
+    if (rc || e != cudaSuccess) return fail("gast_debug_gemm: %s", cudaGetErrorString(rc ? (cudaError_t)rc : e));
+    return 0;
+  }
+  dim3 grid(cdiv(M, 128), cdiv(N, FF_BN));
+  size_t smem = ffma_smem_bytes(EPI_PLAIN, 1, 128, 1);
+  CUDA_OK(cudaFuncSetAttribute((const void*)gemm_ffma_kernel<EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  gemm_ffma_kernel<EPI_PLAIN><<<grid, FF_THREADS, smem, st>>>(p);
+  CUDA_OK(cudaStreamSynchronize(st));
   return 0;
 }

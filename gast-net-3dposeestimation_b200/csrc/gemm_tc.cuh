@@ -1,8 +1,655 @@
-// tcgen05 (5th-gen tensor core) GEMM core -- placeholder until the 3xTF32 kernel lands.
+// tcgen05 (5th-gen tensor core) GEMM core of the lifting path: error-compensated 3xTF32.
+//
+//   D[128 rows, 128 cols] (fp32, TMEM) += A_hi.B_hi + A_hi.B_lo + A_lo.B_hi      per 8-wide k-step
+//
+// where x_hi = tf32(x), x_lo = tf32(x - x_hi).  The dropped A_lo.B_lo term is 2^-22 relative,
+// so the result matches an fp32 FFMA GEMM to ~1e-6 (the parity bar is 1e-4 abs); a single
+// TF32 pass would not.  Same tiles, A-gather and fused epilogues as
+// gemm_ffma.cuh, so both cores are interchangeable per launch.
+//
+// Persistent, warp-specialised CTA (one per SM), 384 threads (registers re-balanced with setmaxnreg):
+//   warps 0-3  A producers : LDG.128 gather of the (frame x joint x channel) tile rows along
+//                            the channel axis -> hi/lo split -> 128B-swizzled K-major smem
+//   warp  8    B producer  : TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) of the pre-split weights
+//   warp  9    MMA issuer  : one thread issues tcgen05.mma.kind::tf32, accumulators in TMEM
+//   warps 4-7  accumulate  : tcgen05.ld every 32-wide K chunk and add it into fp32 REGISTERS
+//              + epilogue    (round-to-nearest), then smem staging for the joint mixing ->
+//                            bias/BN shift/ReLU/residual | SemCH neighbour mix | attention mix
+//
+// Two-level accumulation.  Measured on B200 (tools/tc_probe.py, profiles/r01_tc_numerics.md): the
+// tensor core aligns and TRUNCATES its addends, so a long accumulation chain in TMEM is biased
+// towards zero by ~1 ulp per MMA (K=1536: -1e-5 relative; whole model: 6e-5 abs, MPJPE biased).
+// Therefore the big term A_hi.B_hi is accumulated in TMEM over ONE chunk only (4 MMAs, into a
+// ring of 3 main buffers) and the chunk sums are added in registers with RN; the small terms
+// A_lo.B_hi + A_hi.B_lo (2^-11 of the result, truncation harmless) accumulate over the whole K in
+// a 4th TMEM buffer that is added once per tile.
 #pragma once
+#include <cuda.h>
+#include <vector>
 #include "gast_common.cuh"
+
 namespace gast {
-struct TcWeights { float* hi = nullptr; float* lo = nullptr; };
-inline bool tc_supported(const GemmP&, int, const TcWeights&) { return false; }
-inline int tc_launch(int, cudaStream_t, int, const GemmP&, const TcWeights&) { return (int)cudaErrorNotSupported; }
+
+struct TcWeights {
+  float* hi = nullptr;
+  float* lo = nullptr;
+  CUtensorMap map_hi, map_lo;
+  int N = 0, K = 0;
+  bool ready = false;
+};
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 2;
+constexpr int TC_THREADS = 384;   // 3 warpgroups: A producers | accumulate+epilogue | TMA, MMA, 2 idle
+constexpr int TC_STAGE_BYTES = 4 * 16384;            // A_hi, A_lo, B_hi, B_lo : 128 rows x 128 B each
+constexpr int TC_SLD = 68;                            // staging row stride (floats): conflict-free 16B rows
+constexpr int TC_MAX_NNZ = 64;
+constexpr int TC_JMAX = 20;
+constexpr int TC_OFF_STAGING = TC_STAGES * TC_STAGE_BYTES;
+constexpr int TC_OFF_COEF = TC_OFF_STAGING + 128 * TC_SLD * 4;
+constexpr int TC_OFF_AB = TC_OFF_COEF + TC_MAX_NNZ * TC_SLD * 4;
+constexpr int TC_OFF_BAR = TC_OFF_AB + 128 * 8 * 4;
+constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 128 + 1024;   // 12 mbarriers + tmem ptr   // + alignment slack
+
+// ----------------------------------------------------------------------------------------
+// PTX wrappers
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, kind::tf32, single CTA
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (quadrant base + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row atoms of 1024 B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);       // start address, 16 B units
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset between 8-row atoms
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=128
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                              ((uint32_t)(TC_BM >> 4) << 24);
+
+// ----------------------------------------------------------------------------------------
+// kernel
+// ----------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensorMap map_hi,
+               const __grid_constant__ CUtensorMap map_lo, int n_tiles_n, int total_tiles) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  float* staging = reinterpret_cast<float*>(smem + TC_OFF_STAGING);
+  float* coef_s = reinterpret_cast<float*>(smem + TC_OFF_COEF);
+  float* ab_s = reinterpret_cast<float*>(smem + TC_OFF_AB);
+  const uint32_t bar0 = sbase + TC_OFF_BAR;
+  // barriers: full[2] @0,8  empty[2] @16,24  main_full[3] @32..  main_empty[3] @56..
+  //           corr_full @80  corr_empty @88 ; tmem ptr @96
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + TC_OFF_BAR + 96);
+  constexpr int NMAIN = 3;
+  constexpr uint32_t CORR_COL = NMAIN * TC_BN;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int J = p.J;
+
+  if (tid == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(bar0 + 8 * s, 5);          // 4 A-producer warps + 1 expect_tx arrive
+      mbar_init(bar0 + 16 + 8 * s, 1);     // tcgen05.commit
+    }
+    for (int b = 0; b < NMAIN; ++b) {
+      mbar_init(bar0 + 32 + 8 * b, 1);     // tcgen05.commit
+      mbar_init(bar0 + 56 + 8 * b, 4);     // 4 accumulate/epilogue warps
+    }
+    mbar_init(bar0 + 80, 1);
+    mbar_init(bar0 + 88, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) tmem_alloc(sbase + TC_OFF_BAR + 96, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  int nchunks = 0;
+  for (int s = 0; s < p.nseg; ++s) nchunks += p.seg[s].K / TC_BK;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 152;");
+    // ================================================================= A producers
+    const int c16 = tid & 7;            // 16-byte chunk of the 128-byte row
+    const int r0 = tid >> 3;            // rows r0 + 16*i
+    int fr[8], jj[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { int row = r0 + 16 * i; fr[i] = row / J; jj[i] = row - fr[i] * J; }
+    const uint32_t sw_off = (uint32_t)((c16 ^ (r0 & 7)) << 4);
+    long long roff[8];
+    int c_tile = -1, c_seg = -1;
+    auto ensure = [&](int tile, int sg) {
+      if (tile == c_tile && sg == c_seg) return;
+      c_tile = tile; c_seg = sg;
+      const int f0 = (tile / n_tiles_n) * p.fpt;
+      const int nf = min(p.fpt, p.F - f0);
+      const RowMap mp = p.seg[sg].map;
+      const long long ld = p.seg[sg].ld;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (fr[i] < nf) {
+          int f = f0 + fr[i];
+          int b = f / mp.T_out;
+          int t = f - b * mp.T_out;
+          long long fin = (long long)b * mp.T_in + (long long)t * mp.t_mul + mp.t_off;
+          roff[i] = (fin * J + jj[i]) * ld;
+        } else {
+          roff[i] = -1;
+        }
+      }
+    };
+    auto load = [&](int sg, int k0, float4* v) {
+      const ASeg& sgm = p.seg[sg];
+      const int tap = k0 / sgm.Kc;
+      const float* base = sgm.base + tap * sgm.tap_stride + (k0 - tap * sgm.Kc) + c16 * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        v[i] = (roff[i] >= 0) ? ldg4(base + roff[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    int tile = blockIdx.x, sg = 0, k0 = 0;
+    bool have = tile < total_tiles;
+    float4 cur[8], nxt[8];
+    if (have) { ensure(tile, sg); load(sg, k0, cur); }
+    int stage = 0;
+    uint32_t phase = 0;
+    while (have) {
+      int ntile = tile, nsg = sg, nk0 = k0 + TC_BK;
+      if (nk0 >= p.seg[sg].K) { nk0 = 0; ++nsg; if (nsg >= p.nseg) { nsg = 0; ntile += gridDim.x; } }
+      const bool nhave = ntile < total_tiles;
+      if (nhave) { ensure(ntile, nsg); load(nsg, nk0, nxt); }
+      mbar_wait(bar0 + 16 + 8 * stage, phase ^ 1);
+      unsigned char* a_hi = smem + stage * TC_STAGE_BYTES;
+      unsigned char* a_lo = a_hi + 16384;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = r0 + 16 * i;
+        float4 x = cur[i], h, l;
+        h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
+        l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
+        *reinterpret_cast<float4*>(a_hi + row * 128 + sw_off) = h;
+        *reinterpret_cast<float4*>(a_lo + row * 128 + sw_off) = l;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + 8 * stage);
+      if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+      tile = ntile; sg = nsg; k0 = nk0; have = nhave;
+    }
+  } else if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 8) {
+    // ================================================================= B producer (TMA)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % n_tiles_n) * TC_BN;
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(bar0 + 16 + 8 * stage, phase ^ 1);
+          const uint32_t full = bar0 + 8 * stage;
+          mbar_arrive_expect_tx(full, 2 * 16384);
+          const uint32_t dst = sbase + stage * TC_STAGE_BYTES + 2 * 16384;
+          tma_load_2d(dst, &map_hi, full, c * TC_BK, n0);
+          tma_load_2d(dst + 16384, &map_lo, full, c * TC_BK, n0);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+    } else if (warp == 9) {
+    // ================================================================= MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t mcount = 0;                 // main buffers handed out so far
+      uint32_t tphase = 0;                 // tile parity (corr buffer)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(bar0 + 88, tphase ^ 1);  // corr buffer drained by the epilogue of the previous tile
+        const uint32_t d_corr = tmem_base + CORR_COL;
+        for (int c = 0; c < nchunks; ++c) {
+          const uint32_t mb = mcount % NMAIN;
+          mbar_wait(bar0 + 56 + 8 * mb, ((mcount / NMAIN) & 1) ^ 1);
+          mbar_wait(bar0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t d_main = tmem_base + mb * TC_BN;
+          const uint32_t sa = sbase + stage * TC_STAGE_BYTES;
+          const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + 16384);
+          const uint64_t b_hi = make_smem_desc(sa + 32768), b_lo = make_smem_desc(sa + 49152);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);      // 8 fp32 = 32 B = 2 x 16 B
+            umma_tf32(d_main, a_hi + adv, b_hi + adv, TC_IDESC, k ? 1u : 0u);
+            umma_tf32(d_corr, a_lo + adv, b_hi + adv, TC_IDESC, (c | k) ? 1u : 0u);
+            umma_tf32(d_corr, a_hi + adv, b_lo + adv, TC_IDESC, 1u);
+          }
+          umma_commit(bar0 + 16 + 8 * stage);             // frees the smem stage when the MMAs retire
+          umma_commit(bar0 + 32 + 8 * mb);                // chunk sum ready
+          ++mcount;
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar0 + 80);                           // correction term ready
+        tphase ^= 1;
+      }
+    }
+    __syncwarp();
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // ================================================================= epilogue warps 4..7
+    const int ew = warp - 4;                 // == warp % 4 : TMEM lane quadrant
+    const int et = tid - 128;                // 0..127
+    const int r = ew * 32 + lane;            // tile row of this thread
+    const int fr = r / J, ji = r - fr * J;
+    const int fb = fr * J;                   // first row of this thread's frame
+    uint32_t mcount = 0;
+    uint32_t tphase = 0;
+    const uint32_t lane_off = (uint32_t)(ew * 32) << 16;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int tn = tile % n_tiles_n;
+      const int f0 = (tile / n_tiles_n) * p.fpt;
+      const int nf = min(p.fpt, p.F - f0);
+      const int vrows = nf * J;
+      const int n0 = tn * TC_BN;
+      const bool valid = r < vrows;
+      const long long orow = (long long)(f0 + fr) * J + ji;
+
+      if (EPI == EPI_SEMCH) {
+        const int mask_ = tn / p.tiles_per_mask;
+        const int c0_ = (tn - mask_ * p.tiles_per_mask) * 64;
+        const int nnz_ = p.nbr[mask_].row_ptr[J];
+        // coefficient slab of this tile's 64 channels -> smem (the previous tile's readers are
+        // done: barrier at the end of the loop body)
+        for (int i = et; i < nnz_ * 16; i += 128) {
+          int z = i >> 4, g = (i & 15) * 4;
+          float4 cf = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c0_ + g < p.C) cf = ldg4(p.coef[mask_] + (long long)z * p.C + c0_ + g);
+          *reinterpret_cast<float4*>(coef_s + z * TC_SLD + g) = cf;
+        }
+      }
+      if (EPI == EPI_GLOBAL) {
+        const int H2_ = 2 * p.heads;
+        for (int i = et; i < 128 * H2_; i += 128) {
+          int rr = i / H2_;
+          ab_s[i] = (rr < vrows) ? __ldg(p.ab + ((long long)f0 * J) * H2_ + i) : 0.f;
+        }
+      }
+
+      // ---- level-2 accumulation: chunk sums (TMEM) -> fp32 registers, round-to-nearest adds
+      float acc[TC_BN];
+#pragma unroll
+      for (int i = 0; i < TC_BN; ++i) acc[i] = 0.f;
+      for (int c = 0; c < nchunks; ++c) {
+        const uint32_t mb = mcount % NMAIN;
+        mbar_wait(bar0 + 32 + 8 * mb, (mcount / NMAIN) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + mb * TC_BN + lane_off;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v[32];
+          tmem_ld32(taddr + q * 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[q * 32 + i] += v[i];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + 56 + 8 * mb);
+        ++mcount;
+      }
+      {
+        mbar_wait(bar0 + 80, tphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + CORR_COL + lane_off;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v[32];
+          tmem_ld32(taddr + q * 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[q * 32 + i] += v[i];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + 88);
+        tphase ^= 1;
+      }
+
+      if (EPI == EPI_PLAIN) {
+        if (valid) {
+          const float* resrow = nullptr;
+          if (p.res) {
+            long long fin = map_frame(p.res_map, f0 + fr);
+            resrow = p.res + (fin * J + ji) * (long long)p.res_ld;
+          }
+#pragma unroll
+          for (int g = 0; g < 32; ++g) {
+            const int n = n0 + g * 4;
+            if (n < p.N) {
+              float4 o = make_float4(acc[g * 4], acc[g * 4 + 1], acc[g * 4 + 2], acc[g * 4 + 3]);
+              if (p.bias) { float4 bb = ldg4(p.bias + n); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
+              if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              if (resrow) { float4 rr = ldg4(resrow + n); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+              *reinterpret_cast<float4*>(p.out + orow * p.ld_out + n) = o;
+            }
+          }
+        }
+      } else if (EPI == EPI_SEMCH) {
+        const int mask = tn / p.tiles_per_mask;
+        const int c0 = (tn - mask * p.tiles_per_mask) * 64;
+        const NbrTable& nb = p.nbr[mask];
+        // acc[0..63] = X.W0 (self term), acc[64..127] = X.W1 (neighbour term) -> staging
+#pragma unroll
+        for (int g = 0; g < 16; ++g)
+          *reinterpret_cast<float4*>(staging + r * TC_SLD + g * 4) =
+              make_float4(acc[64 + g * 4], acc[64 + g * 4 + 1], acc[64 + g * 4 + 2], acc[64 + g * 4 + 3]);
+        const float* h0 = acc;
+        epi_bar_sync();
+        if (valid) {
+          const int z0 = nb.row_ptr[ji], z1 = nb.row_ptr[ji + 1];
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {           // 16 channels at a time
+            float o[16];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+              const int c = c0 + gq * 16 + g * 4;
+              if (p.shift && c < p.C) sh = ldg4(p.shift + mask * p.C + c);
+              o[g * 4] = sh.x; o[g * 4 + 1] = sh.y; o[g * 4 + 2] = sh.z; o[g * 4 + 3] = sh.w;
+            }
+            for (int z = z0; z < z1; ++z) {
+              const int jn = nb.col[z];
+              const float* hrow = staging + (fb + jn) * TC_SLD + gq * 16;
+              const float* crow = coef_s + z * TC_SLD + gq * 16;
+              const bool self = (jn == ji);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float4 cf = *reinterpret_cast<const float4*>(crow + g * 4);
+                float4 hv = *reinterpret_cast<const float4*>(hrow + g * 4);
+                if (self) hv = make_float4(h0[gq * 16 + g * 4], h0[gq * 16 + g * 4 + 1], h0[gq * 16 + g * 4 + 2], h0[gq * 16 + g * 4 + 3]);
+                o[g * 4] = fmaf(cf.x, hv.x, o[g * 4]); o[g * 4 + 1] = fmaf(cf.y, hv.y, o[g * 4 + 1]);
+                o[g * 4 + 2] = fmaf(cf.z, hv.z, o[g * 4 + 2]); o[g * 4 + 3] = fmaf(cf.w, hv.w, o[g * 4 + 3]);
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int c = c0 + gq * 16 + g * 4;
+              if (c < p.C) {
+                float4 ov = make_float4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
+                if (p.relu) { ov.x = fmaxf(ov.x, 0.f); ov.y = fmaxf(ov.y, 0.f); ov.z = fmaxf(ov.z, 0.f); ov.w = fmaxf(ov.w, 0.f); }
+                *reinterpret_cast<float4*>(p.out + orow * p.ld_out + mask * p.C + c) = ov;
+              }
+            }
+          }
+        }
+        epi_bar_sync();      // staging / coef slab free for the next tile
+      } else {               // EPI_GLOBAL
+        const int H2 = 2 * p.heads;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int nb0 = n0 + half * 64;
+#pragma unroll
+          for (int g = 0; g < 16; ++g) {
+            const int n = nb0 + g * 4;
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bg && n < p.N) bb = ldg4(p.bg + n);
+            *reinterpret_cast<float4*>(staging + r * TC_SLD + g * 4) =
+                make_float4(acc[half * 64 + g * 4] + bb.x, acc[half * 64 + g * 4 + 1] + bb.y,
+                            acc[half * 64 + g * 4 + 2] + bb.z, acc[half * 64 + g * 4 + 3] + bb.w);
+          }
+          epi_bar_sync();
+          if (valid && nb0 < p.N) {
+            const int nend = min(nb0 + 64, p.N);
+            const int h_lo = nb0 / p.Cg, h_hi = (nend - 1) / p.Cg;
+            for (int h = h_lo; h <= h_hi; ++h) {
+              // attention row of joint ji: softmax_j(LeakyReLU_0.2(a_i + b_j)) + C_k[i,j]
+              float att[TC_JMAX];
+              const float a = ab_s[r * H2 + 2 * h];
+              float mx = -3.4e38f;
+#pragma unroll
+              for (int j = 0; j < TC_JMAX; ++j) {
+                if (j < J) {
+                  float s = a + ab_s[(fb + j) * H2 + 2 * h + 1];
+                  s = (s >= 0.f) ? s : 0.2f * s;
+                  att[j] = s;
+                  mx = fmaxf(mx, s);
+                }
+              }
+              float sum = 0.f;
+#pragma unroll
+              for (int j = 0; j < TC_JMAX; ++j)
+                if (j < J) { att[j] = expf(att[j] - mx); sum += att[j]; }
+              const float inv = 1.f / sum;
+              const float* ck = p.ck + ((long long)h * J + ji) * J;
+#pragma unroll
+              for (int j = 0; j < TC_JMAX; ++j)
+                if (j < J) att[j] = att[j] * inv + __ldg(ck + j);
+              const int cbeg = max(h * p.Cg, nb0), cend = min((h + 1) * p.Cg, nend);
+              for (int n = cbeg; n < cend; n += 4) {
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float* scol = staging + fb * TC_SLD + (n - nb0);
+#pragma unroll
+                for (int j = 0; j < TC_JMAX; ++j) {
+                  if (j < J) {
+                    float4 g4 = *reinterpret_cast<const float4*>(scol + j * TC_SLD);
+                    o.x = fmaf(att[j], g4.x, o.x); o.y = fmaf(att[j], g4.y, o.y);
+                    o.z = fmaf(att[j], g4.z, o.z); o.w = fmaf(att[j], g4.w, o.w);
+                  }
+                }
+                *reinterpret_cast<float4*>(p.out + orow * p.ld_out + n) = o;
+              }
+            }
+          }
+          epi_bar_sync();    // staging free for the next half / tile
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------
+// Residual truncation bias of the 4-MMA chunk accumulation (measured -8.7e-8 relative, K-independent,
+// tools/tc_probe.py): the partial sum after k-step s is truncated by ~0.5 ulp towards zero, i.e. the
+// product of k-step s is under-counted by TC_TRUNC_C * (4 - s).  It is added back through the
+// correction accumulator by folding it into W_lo (it is ~2^-22 of W, far below W_lo's own ulp budget).
+constexpr float TC_TRUNC_C = 3.5e-8f;
+
+__global__ void tc_split_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo,
+                                long long n, int K) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x = w[i];
+  float h = tf32_rna(x);
+  int k = (int)(i % K);
+  float steps_left = (float)(TC_BK / 8 - (k % TC_BK) / 8);
+  hi[i] = h;
+  lo[i] = tf32_rna((x - h) + TC_TRUNC_C * steps_left * h);
+}
+
+typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline tc_encode_fn tc_get_encode() {
+  static tc_encode_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<tc_encode_fn>(p);
+  }
+  return fn;
+}
+
+// W: [N][K] fp32 K-major (device).  Allocates hi/lo once, splits, encodes the TMA maps.
+// Returns 0 on success, a cudaError_t / -1 otherwise.
+inline int tc_prepare_weights(TcWeights& t, const float* W, int N, int K, cudaStream_t st,
+                              std::vector<void*>* owned) {
+  t.ready = false;
+  if (K % TC_BK != 0 || N % 4 != 0) return 0;            // shape not taken by this core (FFMA runs it)
+  tc_encode_fn enc = tc_get_encode();
+  if (!enc) return -1;
+  if (!t.hi || t.N != N || t.K != K) {
+    void* a = nullptr; void* b = nullptr;
+    cudaError_t e = cudaMalloc(&a, sizeof(float) * (size_t)N * K);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMalloc(&b, sizeof(float) * (size_t)N * K);
+    if (e != cudaSuccess) return (int)e;
+    owned->push_back(a); owned->push_back(b);
+    t.hi = (float*)a; t.lo = (float*)b; t.N = N; t.K = K;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r1 = enc(&t.map_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, t.hi, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = enc(&t.map_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, t.lo, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return -1;
+  }
+  long long n = (long long)N * K;
+  tc_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, t.hi, t.lo, n, K);
+  t.ready = true;
+  return 0;
+}
+
+inline bool tc_supported(const GemmP& p, int epi, const TcWeights& t) {
+  if (!t.ready || t.K != p.ldw) return false;
+  if (p.J > TC_JMAX || p.N % 4) return false;
+  for (int s = 0; s < p.nseg; ++s) {
+    const ASeg& sg = p.seg[s];
+    if (sg.K % TC_BK || sg.Kc % TC_BK || sg.ld % 4 || sg.tap_stride % 4) return false;
+    if (reinterpret_cast<uintptr_t>(sg.base) & 15) return false;
+  }
+  if (epi == EPI_SEMCH) {
+    if (p.C % 4) return false;
+    for (int m = 0; m < 2; ++m)
+      if (p.coef[m] && p.nbr[m].row_ptr[p.J] > TC_MAX_NNZ) return false;
+  }
+  if (epi == EPI_GLOBAL && (p.Cg % 4 || p.heads > 4)) return false;
+  return true;
+}
+
+inline int tc_launch(int sm_count, cudaStream_t st, int epi, const GemmP& p, const TcWeights& t) {
+  const int mt = (p.F + p.fpt - 1) / p.fpt;
+  const int nt = (p.N + TC_BN - 1) / TC_BN;
+  const long long total = (long long)mt * nt;
+  if (total > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+  const int grid = (int)(total < sm_count ? total : sm_count);
+  static bool attr_set[3] = {false, false, false};
+  const void* fn = epi == EPI_PLAIN ? (const void*)gemm_tc_kernel<EPI_PLAIN>
+                 : epi == EPI_SEMCH ? (const void*)gemm_tc_kernel<EPI_SEMCH>
+                                    : (const void*)gemm_tc_kernel<EPI_GLOBAL>;
+  if (!attr_set[epi]) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[epi] = true;
+  }
+  if (epi == EPI_PLAIN) gemm_tc_kernel<EPI_PLAIN><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p, t.map_hi, t.map_lo, nt, (int)total);
+  else if (epi == EPI_SEMCH) gemm_tc_kernel<EPI_SEMCH><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p, t.map_hi, t.map_lo, nt, (int)total);
+  else gemm_tc_kernel<EPI_GLOBAL><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p, t.map_hi, t.map_lo, nt, (int)total);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace gast

@@ -16,7 +16,7 @@ KIND_MODEL, KIND_BLOCK, KIND_LOCAL, KIND_MGLOBAL, KIND_SEMCH, KIND_GLOBAL_HEAD =
 SYMBOLS = ['gast_create', 'gast_destroy', 'gast_bind', 'gast_prepare', 'gast_out_frames',
            'gast_receptive_field', 'gast_workspace_bytes', 'gast_forward',
            'gast_last_launch_count', 'gast_last_tc_launch_count', 'gast_set_timing',
-           'gast_get_timings', 'gast_set_gemm_core', 'gast_last_error', 'gast_version']
+           'gast_get_timings', 'gast_set_gemm_core', 'gast_debug_gemm', 'gast_last_error', 'gast_version']
 
 
 class GastCfg(C.Structure):
@@ -73,6 +73,8 @@ def load():
     lib.gast_get_timings.restype = C.c_int32
     lib.gast_set_gemm_core.argtypes = [vp, C.c_int32]
     lib.gast_set_gemm_core.restype = C.c_int
+    lib.gast_debug_gemm.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+    lib.gast_debug_gemm.restype = C.c_int
     lib.gast_last_error.argtypes = []
     lib.gast_last_error.restype = C.c_char_p
     lib.gast_version.argtypes = []

@@ -117,6 +117,12 @@ int32_t gast_get_timings(gast_t* h, int32_t max_n, float* ms, int32_t* kinds);
  * allows), 1 = force the FP32 FFMA core.  Not a fallback switch: both are CUDA paths. */
 int gast_set_gemm_core(gast_t* h, int32_t core);
 
+/* Test/probe entry (not on the forward path): out[M,N] = A[M,K] . W[N,K]^T on one GEMM core
+ * (core 0 = tcgen05 3xTF32, 1 = FFMA; tc_mode 1 = hi.hi product only, to characterise the
+ * tensor core's accumulate rounding).  Synchronises the stream. */
+int gast_debug_gemm(const float* A, const float* W, float* out, int32_t M, int32_t N, int32_t K,
+                    int32_t core, int32_t tc_mode, void* stream);
+
 const char* gast_last_error(void);
 const char* gast_version(void);
 
