@@ -109,19 +109,26 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (quadrant base + i)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (quadrant base + i).
+// Asynchronous: the registers are valid only after tmem_wait_ld(), which names them as in/out
+// operands so that the compiler cannot move their uses above the wait.
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  tmem_ld32_async(taddr, r);
+  tmem_wait_ld(r);
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
@@ -130,6 +137,11 @@ __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
+}
+
+// finite inputs only: add half an ulp of the 10-bit mantissa and clear the 13 low bits
+__device__ __forceinline__ float tf32_rn_fast(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -236,36 +248,52 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       for (int i = 0; i < 8; ++i)
         v[i] = (roff[i] >= 0) ? ldg4(base + roff[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
+    // Load cursor runs up to 3 chunks (48 KB per SM) ahead of the smem ring in REGISTERS: one
+    // chunk per HBM round trip would leave the tensor pipe idle 2/3 of the time (ncu: long_sb
+    // on the first use of the loaded tile, profiles/r01_tc_v1_*).
     int tile = blockIdx.x, sg = 0, k0 = 0;
     bool have = tile < total_tiles;
-    float4 cur[8], nxt[8];
-    if (have) { ensure(tile, sg); load(sg, k0, cur); }
+    auto advance = [&]() {
+      k0 += TC_BK;
+      if (k0 >= p.seg[sg].K) { k0 = 0; ++sg; if (sg >= p.nseg) { sg = 0; tile += gridDim.x; } }
+      have = tile < total_tiles;
+    };
+    float4 buf[3][8];
+    bool valid[3];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      valid[s] = have;
+      if (have) { ensure(tile, sg); load(sg, k0, buf[s]); advance(); }
+    }
     int stage = 0;
     uint32_t phase = 0;
-    while (have) {
-      int ntile = tile, nsg = sg, nk0 = k0 + TC_BK;
-      if (nk0 >= p.seg[sg].K) { nk0 = 0; ++nsg; if (nsg >= p.nseg) { nsg = 0; ntile += gridDim.x; } }
-      const bool nhave = ntile < total_tiles;
-      if (nhave) { ensure(ntile, nsg); load(nsg, nk0, nxt); }
-      mbar_wait(bar0 + 16 + 8 * stage, phase ^ 1);
-      unsigned char* a_hi = smem + stage * TC_STAGE_BYTES;
-      unsigned char* a_lo = a_hi + 16384;
+    bool running = true;
+    while (running) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = r0 + 16 * i;
-        float4 x = cur[i], h, l;
-        h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
-        l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
-        *reinterpret_cast<float4*>(a_hi + row * 128 + sw_off) = h;
-        *reinterpret_cast<float4*>(a_lo + row * 128 + sw_off) = l;
+      for (int s = 0; s < 3; ++s) {
+        if (!valid[s]) { running = false; break; }
+        mbar_wait(bar0 + 16 + 8 * stage, phase ^ 1);
+        unsigned char* a_hi = smem + stage * TC_STAGE_BYTES;
+        unsigned char* a_lo = a_hi + 16384;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = r0 + 16 * i;
+          float4 x = buf[s][i], h, l;
+          // hi = RN to tf32 (11 significant bits); lo = x - hi exactly.  lo is handed over
+          // unrounded: the tensor core truncates it to tf32, an error <= 2^-21 |x| whose sign
+          // is that of -lo, i.e. unbiased because hi was rounded to nearest.
+          h.x = tf32_rn_fast(x.x); h.y = tf32_rn_fast(x.y); h.z = tf32_rn_fast(x.z); h.w = tf32_rn_fast(x.w);
+          l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+          *reinterpret_cast<float4*>(a_hi + row * 128 + sw_off) = h;
+          *reinterpret_cast<float4*>(a_lo + row * 128 + sw_off) = l;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + 8 * stage);
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        valid[s] = have;
+        if (have) { ensure(tile, sg); load(sg, k0, buf[s]); advance(); }
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar0 + 8 * stage);
-      if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-      tile = ntile; sg = nsg; k0 = nk0; have = nhave;
     }
   } else if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -376,11 +404,17 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         tc_fence_after();
         const uint32_t taddr = tmem_base + mb * TC_BN + lane_off;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float v[32];
-          tmem_ld32(taddr + q * 32, v);
+        for (int q = 0; q < 4; q += 2) {
+          uint32_t va[32], vb[32];
+          tmem_ld32_async(taddr + q * 32, va);
+          tmem_ld32_async(taddr + q * 32 + 32, vb);
+          tmem_wait_ld(va);
+          tmem_wait_ld(vb);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[q * 32 + i] += v[i];
+          for (int i = 0; i < 32; ++i) {
+            acc[q * 32 + i] += __uint_as_float(va[i]);
+            acc[q * 32 + 32 + i] += __uint_as_float(vb[i]);
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -392,11 +426,17 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         tc_fence_after();
         const uint32_t taddr = tmem_base + CORR_COL + lane_off;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float v[32];
-          tmem_ld32(taddr + q * 32, v);
+        for (int q = 0; q < 4; q += 2) {
+          uint32_t va[32], vb[32];
+          tmem_ld32_async(taddr + q * 32, va);
+          tmem_ld32_async(taddr + q * 32 + 32, vb);
+          tmem_wait_ld(va);
+          tmem_wait_ld(vb);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[q * 32 + i] += v[i];
+          for (int i = 0; i < 32; ++i) {
+            acc[q * 32 + i] += __uint_as_float(va[i]);
+            acc[q * 32 + 32 + i] += __uint_as_float(vb[i]);
+          }
         }
         tc_fence_before();
         __syncwarp();
