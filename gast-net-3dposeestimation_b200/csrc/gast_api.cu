@@ -829,7 +829,7 @@ static int prepare_tc(gast_handle* h, cudaStream_t st) {
 // for the numerics of the tensor-core path; not used by the forward).
 // ------------------------------------------------------------------------------------------
 extern "C" int gast_debug_gemm(const float* A, const float* W, float* out, int32_t M, int32_t N, int32_t K,
-                               int32_t core, int32_t tc_mode, void* stream) {
+                               int32_t core, int32_t tc_mode, int32_t reps, float* ms_out, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (M <= 0 || N <= 0 || K <= 0 || N % 4 || K % 4) return fail("gast_debug_gemm: bad shape");
   GemmP p;
@@ -840,28 +840,46 @@ extern "C" int gast_debug_gemm(const float* A, const float* W, float* out, int32
   p.seg[0].base = A; p.seg[0].ld = K; p.seg[0].K = K; p.seg[0].Kc = K; p.seg[0].tap_stride = 0;
   p.seg[0].map = RowMap{1, 1, 1, 0};
   p.W = W; p.ldw = K; p.N = N; p.out = out; p.ld_out = N;
-  p.tc_mode = tc_mode;
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  int rc = 0;
+  std::vector<void*> owned;
+  TcWeights t;
+  int sms = 148;
   if (core == 0) {
-    int dev = 0, sms = 148;
+    int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    TcWeights t;
-    std::vector<void*> owned;
-    int rc = tc_prepare_weights(t, W, N, K, st, &owned);
+    rc = tc_prepare_weights(t, W, N, K, st, &owned);
     if (rc || !t.ready || !tc_supported(p, EPI_PLAIN, t)) {
       for (void* q : owned) cudaFree(q);
       return fail("gast_debug_gemm: shape not supported by the tcgen05 core (rc=%d)", rc);
     }
-    rc = tc_launch(sms, st, EPI_PLAIN, p, t);
-    cudaError_t e = cudaStreamSynchronize(st);
-    for (void* q : owned) cudaFree(q);
-    if (rc || e != cudaSuccess) return fail("gast_debug_gemm: %s", cudaGetErrorString(rc ? (cudaError_t)rc : e));
-    return 0;
+  } else {
+    cudaFuncSetAttribute((const void*)gemm_ffma_kernel<EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   }
-  dim3 grid(cdiv(M, 128), cdiv(N, FF_BN));
-  size_t smem = ffma_smem_bytes(EPI_PLAIN, 1, 128, 1);
-  CUDA_OK(cudaFuncSetAttribute((const void*)gemm_ffma_kernel<EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  gemm_ffma_kernel<EPI_PLAIN><<<grid, FF_THREADS, smem, st>>>(p);
-  CUDA_OK(cudaStreamSynchronize(st));
+  auto launch = [&]() -> int {
+    if (core == 0) return tc_launch(sms, st, EPI_PLAIN, p, t, tc_mode);
+    dim3 grid(cdiv(M, 128), cdiv(N, FF_BN));
+    gemm_ffma_kernel<EPI_PLAIN><<<grid, FF_THREADS, ffma_smem_bytes(EPI_PLAIN, 1, 128, 1), st>>>(p);
+    return (int)cudaGetLastError();
+  };
+  rc = launch();
+  if (!rc && reps > 0) {
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < reps && !rc; ++i) rc = launch();
+    cudaEventRecord(e1, st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (!rc && e == cudaSuccess && reps > 0 && ms_out) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = ms / reps;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  for (void* q : owned) cudaFree(q);
+  if (rc || e != cudaSuccess) return fail("gast_debug_gemm: %s", cudaGetErrorString(rc ? (cudaError_t)rc : e));
   return 0;
 }

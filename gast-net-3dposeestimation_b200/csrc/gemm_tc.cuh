@@ -38,17 +38,20 @@ struct TcWeights {
   bool ready = false;
 };
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 2;
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;
+constexpr int TC_BSTAGES = 4;   // B (weights) ring in shared memory, filled by TMA
+constexpr int TC_ASTAGES = 2;
+constexpr int TC_FLUSH = 4;     // K chunks accumulated in TMEM before the sum is flushed to registers   // A (activations) ring in TENSOR MEMORY, filled by tcgen05.st
 constexpr int TC_THREADS = 384;   // 3 warpgroups: A producers | accumulate+epilogue | TMA, MMA, 2 idle
-constexpr int TC_STAGE_BYTES = 4 * 16384;            // A_hi, A_lo, B_hi, B_lo : 128 rows x 128 B each
+constexpr int TC_STAGE_BYTES = 2 * 16384;            // B_hi, B_lo : 128 rows x 128 B each
 constexpr int TC_SLD = 68;                            // staging row stride (floats): conflict-free 16B rows
 constexpr int TC_MAX_NNZ = 64;
 constexpr int TC_JMAX = 20;
-constexpr int TC_OFF_STAGING = TC_STAGES * TC_STAGE_BYTES;
+constexpr int TC_OFF_STAGING = TC_BSTAGES * TC_STAGE_BYTES;
 constexpr int TC_OFF_COEF = TC_OFF_STAGING + 128 * TC_SLD * 4;
 constexpr int TC_OFF_AB = TC_OFF_COEF + TC_MAX_NNZ * TC_SLD * 4;
 constexpr int TC_OFF_BAR = TC_OFF_AB + 128 * 8 * 4;
-constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 128 + 1024;   // 12 mbarriers + tmem ptr   // + alignment slack
+constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 256 + 1024;   // 12 mbarriers + tmem ptr   // + alignment slack
 
 // ----------------------------------------------------------------------------------------
 // PTX wrappers
@@ -105,6 +108,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+// same with the A operand read from tensor memory (TS form): halves the shared-memory
+// traffic of the MMA, which at M=N=128 otherwise saturates the 128 B/clk smem port by itself
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -125,6 +138,15 @@ __device__ __forceinline__ void tmem_wait_ld(uint32_t* r) {
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
                :: "memory");
 }
+// registers -> tensor memory: thread i of the warp writes lane (quadrant base + i), 32 columns
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
+      :: "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
   tmem_ld32_async(taddr, r);
@@ -157,6 +179,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
+// Tensor-memory map (512 columns x 128 lanes x 32 bit):
+//   [0,256)   main accumulator ring (2 x 128): A_hi.B_hi of ONE 32-wide K chunk
+//   [256,384) correction accumulator: A_lo.B_hi + A_hi.B_lo over the whole K
+//   [384,512) A operand ring (2 stages x {hi 32 cols, lo 32 cols}): row m in lane m, k in columns
+constexpr uint32_t TC_NMAIN = 2;
+constexpr uint32_t TC_CORR_COL = 256;
+constexpr uint32_t TC_A_COL = 384;
+
 // instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=128
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
                               ((uint32_t)(TC_BM >> 4) << 24);
@@ -164,7 +194,9 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(T
 // ----------------------------------------------------------------------------------------
 // kernel
 // ----------------------------------------------------------------------------------------
-template <int EPI>
+// DBG != 0 builds timing-experiment variants (tools/tc_probe.py --perf): 1 = no TMEM->register
+// flush, 2 = no global A loads, 3 = main MMA only, 4 = no tcgen05.st of A, 5 = 1+2+4.
+template <int EPI, int DBG = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap map_lo, int n_tiles_n, int total_tiles) {
@@ -176,11 +208,13 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
   float* coef_s = reinterpret_cast<float*>(smem + TC_OFF_COEF);
   float* ab_s = reinterpret_cast<float*>(smem + TC_OFF_AB);
   const uint32_t bar0 = sbase + TC_OFF_BAR;
-  // barriers: full[2] @0,8  empty[2] @16,24  main_full[3] @32..  main_empty[3] @56..
-  //           corr_full @80  corr_empty @88 ; tmem ptr @96
-  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + TC_OFF_BAR + 96);
-  constexpr int NMAIN = 3;
-  constexpr uint32_t CORR_COL = NMAIN * TC_BN;
+  // mbarriers (8 B each):  b_full[4] @0  b_empty[4] @32  a_full[2] @64  a_empty[2] @80
+  //                        main_full[2] @96  main_empty[2] @112  corr_full @128  corr_empty @136 ; tmem ptr @144
+  constexpr uint32_t BB_FULL = 0, BB_EMPTY = 32, BA_FULL = 64, BA_EMPTY = 80, BM_FULL = 96, BM_EMPTY = 112,
+                     BC_FULL = 128, BC_EMPTY = 136, B_TMEMPTR = 144;
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + TC_OFF_BAR + B_TMEMPTR);
+  constexpr uint32_t NMAIN = TC_NMAIN;
+  constexpr uint32_t CORR_COL = TC_CORR_COL;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -188,19 +222,23 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
   const int J = p.J;
 
   if (tid == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(bar0 + 8 * s, 5);          // 4 A-producer warps + 1 expect_tx arrive
-      mbar_init(bar0 + 16 + 8 * s, 1);     // tcgen05.commit
+    for (int s = 0; s < TC_BSTAGES; ++s) {
+      mbar_init(bar0 + BB_FULL + 8 * s, 1);     // expect_tx arrive + TMA bytes
+      mbar_init(bar0 + BB_EMPTY + 8 * s, 1);    // tcgen05.commit
     }
-    for (int b = 0; b < NMAIN; ++b) {
-      mbar_init(bar0 + 32 + 8 * b, 1);     // tcgen05.commit
-      mbar_init(bar0 + 56 + 8 * b, 4);     // 4 accumulate/epilogue warps
+    for (int s = 0; s < TC_ASTAGES; ++s) {
+      mbar_init(bar0 + BA_FULL + 8 * s, 4);     // 4 A-producer warps
+      mbar_init(bar0 + BA_EMPTY + 8 * s, 1);    // tcgen05.commit
     }
-    mbar_init(bar0 + 80, 1);
-    mbar_init(bar0 + 88, 4);
+    for (int b = 0; b < (int)NMAIN; ++b) {
+      mbar_init(bar0 + BM_FULL + 8 * b, 1);     // tcgen05.commit
+      mbar_init(bar0 + BM_EMPTY + 8 * b, 4);    // 4 accumulate/epilogue warps
+    }
+    mbar_init(bar0 + BC_FULL, 1);
+    mbar_init(bar0 + BC_EMPTY, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) tmem_alloc(sbase + TC_OFF_BAR + 96, 512);
+  if (warp == 9) tmem_alloc(sbase + TC_OFF_BAR + B_TMEMPTR, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -212,13 +250,13 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 152;");
     // ================================================================= A producers
-    const int c16 = tid & 7;            // 16-byte chunk of the 128-byte row
-    const int r0 = tid >> 3;            // rows r0 + 16*i
-    int fr[8], jj[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { int row = r0 + 16 * i; fr[i] = row / J; jj[i] = row - fr[i] * J; }
-    const uint32_t sw_off = (uint32_t)((c16 ^ (r0 & 7)) << 4);
-    long long roff[8];
+    // thread t owns tile row t (== TMEM lane t): it loads its 32-float slice of the K chunk
+    // (8 x LDG.128, 128 contiguous bytes along the channel axis), splits hi/lo and writes both to
+    // the A ring in tensor memory with tcgen05.st.
+    const int row = tid;
+    const int fr = row / J, jj = row - fr * J;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    long long roff = -1;
     int c_tile = -1, c_seg = -1;
     auto ensure = [&](int tile, int sg) {
       if (tile == c_tile && sg == c_seg) return;
@@ -226,30 +264,26 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       const int f0 = (tile / n_tiles_n) * p.fpt;
       const int nf = min(p.fpt, p.F - f0);
       const RowMap mp = p.seg[sg].map;
-      const long long ld = p.seg[sg].ld;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (fr[i] < nf) {
-          int f = f0 + fr[i];
-          int b = f / mp.T_out;
-          int t = f - b * mp.T_out;
-          long long fin = (long long)b * mp.T_in + (long long)t * mp.t_mul + mp.t_off;
-          roff[i] = (fin * J + jj[i]) * ld;
-        } else {
-          roff[i] = -1;
-        }
+      if (fr < nf) {
+        int f = f0 + fr;
+        int b = f / mp.T_out;
+        int t = f - b * mp.T_out;
+        long long fin = (long long)b * mp.T_in + (long long)t * mp.t_mul + mp.t_off;
+        roff = (fin * J + jj) * (long long)p.seg[sg].ld;
+      } else {
+        roff = -1;
       }
     };
     auto load = [&](int sg, int k0, float4* v) {
       const ASeg& sgm = p.seg[sg];
       const int tap = k0 / sgm.Kc;
-      const float* base = sgm.base + tap * sgm.tap_stride + (k0 - tap * sgm.Kc) + c16 * 4;
+      const float* src = sgm.base + tap * sgm.tap_stride + (k0 - tap * sgm.Kc) + roff;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        v[i] = (roff[i] >= 0) ? ldg4(base + roff[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = (roff >= 0 && DBG != 2 && DBG != 5) ? ldg4(src + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    // Load cursor runs up to 3 chunks (48 KB per SM) ahead of the smem ring in REGISTERS: one
-    // chunk per HBM round trip would leave the tensor pipe idle 2/3 of the time (ncu: long_sb
+    // Load cursor runs up to 3 chunks (48 KB per SM) ahead of the TMEM ring in REGISTERS: one
+    // chunk per HBM round trip would leave the tensor pipe idle most of the time (ncu: long_sb
     // on the first use of the loaded tile, profiles/r01_tc_v1_*).
     int tile = blockIdx.x, sg = 0, k0 = 0;
     bool have = tile < total_tiles;
@@ -272,25 +306,31 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
         if (!valid[s]) { running = false; break; }
-        mbar_wait(bar0 + 16 + 8 * stage, phase ^ 1);
-        unsigned char* a_hi = smem + stage * TC_STAGE_BYTES;
-        unsigned char* a_lo = a_hi + 16384;
+        uint32_t hi[32], lo[32];
+        // hi = RN to tf32 (11 significant bits); lo = x - hi exactly.  lo is handed over
+        // unrounded: the tensor core truncates it to tf32, an error <= 2^-21 |x| whose sign
+        // is that of -lo, i.e. unbiased because hi was rounded to nearest.
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int row = r0 + 16 * i;
-          float4 x = buf[s][i], h, l;
-          // hi = RN to tf32 (11 significant bits); lo = x - hi exactly.  lo is handed over
-          // unrounded: the tensor core truncates it to tf32, an error <= 2^-21 |x| whose sign
-          // is that of -lo, i.e. unbiased because hi was rounded to nearest.
-          h.x = tf32_rn_fast(x.x); h.y = tf32_rn_fast(x.y); h.z = tf32_rn_fast(x.z); h.w = tf32_rn_fast(x.w);
-          l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
-          *reinterpret_cast<float4*>(a_hi + row * 128 + sw_off) = h;
-          *reinterpret_cast<float4*>(a_lo + row * 128 + sw_off) = l;
+          const float4 x = buf[s][i];
+          float h;
+          h = tf32_rn_fast(x.x); hi[4 * i + 0] = __float_as_uint(h); lo[4 * i + 0] = __float_as_uint(x.x - h);
+          h = tf32_rn_fast(x.y); hi[4 * i + 1] = __float_as_uint(h); lo[4 * i + 1] = __float_as_uint(x.y - h);
+          h = tf32_rn_fast(x.z); hi[4 * i + 2] = __float_as_uint(h); lo[4 * i + 2] = __float_as_uint(x.z - h);
+          h = tf32_rn_fast(x.w); hi[4 * i + 3] = __float_as_uint(h); lo[4 * i + 3] = __float_as_uint(x.w - h);
         }
-        fence_proxy_async_smem();
+        mbar_wait(bar0 + BA_EMPTY + 8 * stage, phase ^ 1);
+        tc_fence_after();
+        const uint32_t ta = tmem_base + lane_off + TC_A_COL + stage * 64;
+        if (DBG != 4 && DBG != 5) {
+          tmem_st32(ta, hi);
+          tmem_st32(ta + 32, lo);
+          tmem_wait_st();
+        }
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar0 + 8 * stage);
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        if (lane == 0) mbar_arrive(bar0 + BA_FULL + 8 * stage);
+        if (++stage == TC_ASTAGES) { stage = 0; phase ^= 1; }
         valid[s] = have;
         if (have) { ensure(tile, sg); load(sg, k0, buf[s]); advance(); }
       }
@@ -305,13 +345,13 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = (tile % n_tiles_n) * TC_BN;
         for (int c = 0; c < nchunks; ++c) {
-          mbar_wait(bar0 + 16 + 8 * stage, phase ^ 1);
-          const uint32_t full = bar0 + 8 * stage;
+          mbar_wait(bar0 + BB_EMPTY + 8 * stage, phase ^ 1);
+          const uint32_t full = bar0 + BB_FULL + 8 * stage;
           mbar_arrive_expect_tx(full, 2 * 16384);
-          const uint32_t dst = sbase + stage * TC_STAGE_BYTES + 2 * 16384;
+          const uint32_t dst = sbase + stage * TC_STAGE_BYTES;
           tma_load_2d(dst, &map_hi, full, c * TC_BK, n0);
           tma_load_2d(dst + 16384, &map_lo, full, c * TC_BK, n0);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == TC_BSTAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -319,35 +359,43 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     } else if (warp == 9) {
     // ================================================================= MMA issuer
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int bs = 0, as = 0;
+      uint32_t bphase = 0, aphase = 0;
       uint32_t mcount = 0;                 // main buffers handed out so far
       uint32_t tphase = 0;                 // tile parity (corr buffer)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(bar0 + 88, tphase ^ 1);  // corr buffer drained by the epilogue of the previous tile
+        mbar_wait(bar0 + BC_EMPTY, tphase ^ 1);  // corr buffer drained by the epilogue of the previous tile
         const uint32_t d_corr = tmem_base + CORR_COL;
         for (int c = 0; c < nchunks; ++c) {
           const uint32_t mb = mcount % NMAIN;
-          mbar_wait(bar0 + 56 + 8 * mb, ((mcount / NMAIN) & 1) ^ 1);
-          mbar_wait(bar0 + 8 * stage, phase);
+          const int cg = c % TC_FLUSH;                    // position in the flush group
+          if (cg == 0) mbar_wait(bar0 + BM_EMPTY + 8 * mb, ((mcount / NMAIN) & 1) ^ 1);
+          mbar_wait(bar0 + BA_FULL + 8 * as, aphase);
+          mbar_wait(bar0 + BB_FULL + 8 * bs, bphase);
           tc_fence_after();
           const uint32_t d_main = tmem_base + mb * TC_BN;
-          const uint32_t sa = sbase + stage * TC_STAGE_BYTES;
-          const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + 16384);
-          const uint64_t b_hi = make_smem_desc(sa + 32768), b_lo = make_smem_desc(sa + 49152);
+          const uint32_t a_hi = tmem_base + TC_A_COL + as * 64, a_lo = a_hi + 32;
+          const uint32_t sb = sbase + bs * TC_STAGE_BYTES;
+          const uint64_t b_hi = make_smem_desc(sb), b_lo = make_smem_desc(sb + 16384);
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {
             const uint64_t adv = (uint64_t)(k * 2);      // 8 fp32 = 32 B = 2 x 16 B
-            umma_tf32(d_main, a_hi + adv, b_hi + adv, TC_IDESC, k ? 1u : 0u);
-            umma_tf32(d_corr, a_lo + adv, b_hi + adv, TC_IDESC, (c | k) ? 1u : 0u);
-            umma_tf32(d_corr, a_hi + adv, b_lo + adv, TC_IDESC, 1u);
+            umma_tf32_ts(d_main, a_hi + 8 * k, b_hi + adv, TC_IDESC, (cg | k) ? 1u : 0u);
+            if (DBG != 3) {
+              umma_tf32_ts(d_corr, a_lo + 8 * k, b_hi + adv, TC_IDESC, (c | k) ? 1u : 0u);
+              umma_tf32_ts(d_corr, a_hi + 8 * k, b_lo + adv, TC_IDESC, 1u);
+            }
           }
-          umma_commit(bar0 + 16 + 8 * stage);             // frees the smem stage when the MMAs retire
-          umma_commit(bar0 + 32 + 8 * mb);                // chunk sum ready
-          ++mcount;
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          umma_commit(bar0 + BB_EMPTY + 8 * bs);          // frees the B smem stage when the MMAs retire
+          umma_commit(bar0 + BA_EMPTY + 8 * as);          // frees the A tmem stage
+          if (cg == TC_FLUSH - 1 || c == nchunks - 1) {
+            umma_commit(bar0 + BM_FULL + 8 * mb);         // group sum ready
+            ++mcount;
+          }
+          if (++bs == TC_BSTAGES) { bs = 0; bphase ^= 1; }
+          if (++as == TC_ASTAGES) { as = 0; aphase ^= 1; }
         }
-        umma_commit(bar0 + 80);                           // correction term ready
+        umma_commit(bar0 + BC_FULL);                      // correction term ready
         tphase ^= 1;
       }
     }
@@ -398,13 +446,14 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       float acc[TC_BN];
 #pragma unroll
       for (int i = 0; i < TC_BN; ++i) acc[i] = 0.f;
-      for (int c = 0; c < nchunks; ++c) {
+      const int ngroups = (nchunks + TC_FLUSH - 1) / TC_FLUSH;
+      for (int c = 0; c < ngroups; ++c) {
         const uint32_t mb = mcount % NMAIN;
-        mbar_wait(bar0 + 32 + 8 * mb, (mcount / NMAIN) & 1);
+        mbar_wait(bar0 + BM_FULL + 8 * mb, (mcount / NMAIN) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + mb * TC_BN + lane_off;
 #pragma unroll
-        for (int q = 0; q < 4; q += 2) {
+        for (int q = 0; q < ((DBG == 1 || DBG == 5) ? 0 : 4); q += 2) {
           uint32_t va[32], vb[32];
           tmem_ld32_async(taddr + q * 32, va);
           tmem_ld32_async(taddr + q * 32 + 32, vb);
@@ -418,15 +467,15 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar0 + 56 + 8 * mb);
+        if (lane == 0) mbar_arrive(bar0 + BM_EMPTY + 8 * mb);
         ++mcount;
       }
       {
-        mbar_wait(bar0 + 80, tphase);
+        mbar_wait(bar0 + BC_FULL, tphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + CORR_COL + lane_off;
 #pragma unroll
-        for (int q = 0; q < 4; q += 2) {
+        for (int q = 0; q < ((DBG == 1 || DBG == 5) ? 0 : 4); q += 2) {
           uint32_t va[32], vb[32];
           tmem_ld32_async(taddr + q * 32, va);
           tmem_ld32_async(taddr + q * 32 + 32, vb);
@@ -440,7 +489,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar0 + 88);
+        if (lane == 0) mbar_arrive(bar0 + BC_EMPTY);
         tphase ^= 1;
       }
 
@@ -586,10 +635,11 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
 // ----------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------
-// Residual truncation bias of the 4-MMA chunk accumulation (measured -8.7e-8 relative, K-independent,
-// tools/tc_probe.py): the partial sum after k-step s is truncated by ~0.5 ulp towards zero, i.e. the
-// product of k-step s is under-counted by TC_TRUNC_C * (4 - s).  It is added back through the
-// correction accumulator by folding it into W_lo (it is ~2^-22 of W, far below W_lo's own ulp budget).
+// Residual truncation bias of the in-TMEM accumulation of one flush group (measured -8.7e-8 relative
+// per 4 MMAs, tools/tc_probe.py): the partial sum after every k-step is truncated by ~0.5 ulp towards
+// zero, i.e. the product of k-step s is under-counted by TC_TRUNC_C * (steps left in its group).
+// It is added back through the correction accumulator by folding it into W_lo (it is <= 2^-20 of W,
+// within W_lo's own rounding budget).
 constexpr float TC_TRUNC_C = 3.5e-8f;
 
 __global__ void tc_split_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo,
@@ -598,8 +648,12 @@ __global__ void tc_split_kernel(const float* __restrict__ w, float* __restrict__
   if (i >= n) return;
   float x = w[i];
   float h = tf32_rna(x);
-  int k = (int)(i % K);
-  float steps_left = (float)(TC_BK / 8 - (k % TC_BK) / 8);
+  const int k = (int)(i % K);
+  const int nchunks = K / TC_BK;
+  const int c = k / TC_BK, g = c / TC_FLUSH;
+  const int glen = min(TC_FLUSH, nchunks - g * TC_FLUSH);            // chunks in this flush group
+  const int s = (c - g * TC_FLUSH) * (TC_BK / 8) + (k % TC_BK) / 8;  // k-step index inside the group
+  const float steps_left = (float)(glen * (TC_BK / 8) - s);          // truncations this product still sees
   hi[i] = h;
   lo[i] = tf32_rna((x - h) + TC_TRUNC_C * steps_left * h);
 }
@@ -671,24 +725,44 @@ inline bool tc_supported(const GemmP& p, int epi, const TcWeights& t) {
   return true;
 }
 
-inline int tc_launch(int sm_count, cudaStream_t st, int epi, const GemmP& p, const TcWeights& t) {
+template <int DBG>
+inline int tc_launch_dbg(int grid, cudaStream_t st, const GemmP& p, const TcWeights& t, int nt, int total) {
+  cudaError_t e = cudaFuncSetAttribute((const void*)gemm_tc_kernel<EPI_PLAIN, DBG>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
+  gemm_tc_kernel<EPI_PLAIN, DBG><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p, t.map_hi, t.map_lo, nt, total);
+  return (int)cudaGetLastError();
+}
+
+inline int tc_launch(int sm_count, cudaStream_t st, int epi, const GemmP& p, const TcWeights& t, int dbg = 0) {
   const int mt = (p.F + p.fpt - 1) / p.fpt;
   const int nt = (p.N + TC_BN - 1) / TC_BN;
   const long long total = (long long)mt * nt;
   if (total > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
   const int grid = (int)(total < sm_count ? total : sm_count);
+  if (dbg) {
+    if (epi != EPI_PLAIN) return (int)cudaErrorInvalidValue;
+    switch (dbg) {
+      case 1: return tc_launch_dbg<1>(grid, st, p, t, nt, (int)total);
+      case 2: return tc_launch_dbg<2>(grid, st, p, t, nt, (int)total);
+      case 3: return tc_launch_dbg<3>(grid, st, p, t, nt, (int)total);
+      case 4: return tc_launch_dbg<4>(grid, st, p, t, nt, (int)total);
+      case 5: return tc_launch_dbg<5>(grid, st, p, t, nt, (int)total);
+      default: return (int)cudaErrorInvalidValue;
+    }
+  }
   static bool attr_set[3] = {false, false, false};
-  const void* fn = epi == EPI_PLAIN ? (const void*)gemm_tc_kernel<EPI_PLAIN>
-                 : epi == EPI_SEMCH ? (const void*)gemm_tc_kernel<EPI_SEMCH>
-                                    : (const void*)gemm_tc_kernel<EPI_GLOBAL>;
+  const void* fn = epi == EPI_PLAIN ? (const void*)gemm_tc_kernel<EPI_PLAIN, 0>
+                 : epi == EPI_SEMCH ? (const void*)gemm_tc_kernel<EPI_SEMCH, 0>
+                                    : (const void*)gemm_tc_kernel<EPI_GLOBAL, 0>;
   if (!attr_set[epi]) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set[epi] = true;
   }
-  if (epi == EPI_PLAIN) gemm_tc_kernel<EPI_PLAIN><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p, t.map_hi, t.map_lo, nt, (int)total);
-  else if (epi == EPI_SEMCH) gemm_tc_kernel<EPI_SEMCH><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p, t.map_hi, t.map_lo, nt, (int)total);
-  else gemm_tc_kernel<EPI_GLOBAL><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p, t.map_hi, t.map_lo, nt, (int)total);
+  if (epi == EPI_PLAIN) gemm_tc_kernel<EPI_PLAIN, 0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p, t.map_hi, t.map_lo, nt, (int)total);
+  else if (epi == EPI_SEMCH) gemm_tc_kernel<EPI_SEMCH, 0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p, t.map_hi, t.map_lo, nt, (int)total);
+  else gemm_tc_kernel<EPI_GLOBAL, 0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p, t.map_hi, t.map_lo, nt, (int)total);
   return (int)cudaGetLastError();
 }
 

@@ -73,7 +73,8 @@ def load():
     lib.gast_get_timings.restype = C.c_int32
     lib.gast_set_gemm_core.argtypes = [vp, C.c_int32]
     lib.gast_set_gemm_core.restype = C.c_int
-    lib.gast_debug_gemm.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+    lib.gast_debug_gemm.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.POINTER(C.c_float), vp]
     lib.gast_debug_gemm.restype = C.c_int
     lib.gast_last_error.argtypes = []
     lib.gast_last_error.restype = C.c_char_p

@@ -118,10 +118,11 @@ int32_t gast_get_timings(gast_t* h, int32_t max_n, float* ms, int32_t* kinds);
 int gast_set_gemm_core(gast_t* h, int32_t core);
 
 /* Test/probe entry (not on the forward path): out[M,N] = A[M,K] . W[N,K]^T on one GEMM core
- * (core 0 = tcgen05 3xTF32, 1 = FFMA; tc_mode 1 = hi.hi product only, to characterise the
- * tensor core's accumulate rounding).  Synchronises the stream. */
+ * (core 0 = tcgen05 3xTF32, 1 = FFMA).  tc_mode != 0 selects a timing-experiment variant of the
+ * tcgen05 kernel (parts disabled; results invalid).  Runs once, then `reps` timed launches
+ * (CUDA events) whose mean duration is written to *ms_out (host).  Synchronises the stream. */
 int gast_debug_gemm(const float* A, const float* W, float* out, int32_t M, int32_t N, int32_t K,
-                    int32_t core, int32_t tc_mode, void* stream);
+                    int32_t core, int32_t tc_mode, int32_t reps, float* ms_out, void* stream);
 
 const char* gast_last_error(void);
 const char* gast_version(void);

@@ -28,11 +28,29 @@ def gemm(A, W, core, mode):
     M, K = A.shape
     N = W.shape[0]
     o = torch.empty((M, N), dtype=torch.float32, device='cuda')
-    rc = lib.gast_debug_gemm(a.data_ptr(), w.data_ptr(), o.data_ptr(), M, N, K, core, mode,
+    rc = lib.gast_debug_gemm(a.data_ptr(), w.data_ptr(), o.data_ptr(), M, N, K, core, mode, 0, None,
                              torch.cuda.current_stream().cuda_stream)
     if rc:
         raise RuntimeError(_lib.last_error())
     return o.cpu().numpy()
+
+
+def perf():
+    """time the tcgen05 kernel and its experiment variants on the lifting path's GEMM shapes"""
+    rs = np.random.RandomState(1)
+    for (M, N, K) in ((674176, 256, 384), (674176, 128, 128), (224768, 512, 768), (75008, 1024, 1536)):
+        a = torch.from_numpy(rs.standard_normal((M, K)).astype(np.float32)).cuda()
+        w = torch.from_numpy(rs.standard_normal((N, K)).astype(np.float32)).cuda()
+        o = torch.empty((M, N), dtype=torch.float32, device='cuda')
+        mma_bound = 3.0 * (-(-M // 128) * 128) * (-(-N // 128) * 128) * K / (2048.0 * 148 * 1.9e9) * 1e3
+        line = 'M=%d N=%d K=%d  MMA-bound %.3f ms |' % (M, N, K, mma_bound)
+        for core, mode, name in ((1, 0, 'ffma'), (0, 0, 'tc'), (0, 1, 'noflush'), (0, 2, 'noAload'), (0, 3, 'mainonly'),
+                                 (0, 4, 'noSTTM'), (0, 5, 'mma+B only')):
+            ms = C.c_float(0)
+            rc = lib.gast_debug_gemm(a.data_ptr(), w.data_ptr(), o.data_ptr(), M, N, K, core, mode, 5, C.byref(ms),
+                                     torch.cuda.current_stream().cuda_stream)
+            line += ' %s %.3f' % (name, ms.value) if rc == 0 else ' %s ERR(%s)' % (name, _lib.last_error()[:40])
+        print(line, flush=True)
 
 
 def stats(name, D, ref):
@@ -77,4 +95,7 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == '--perf':
+        perf()
+    else:
+        main()
