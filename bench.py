@@ -101,36 +101,42 @@ def build_model(device):
     return m.to(device).eval()
 
 
+_CPU_STATE = {}
+
+
 def cpu_port_clips_per_s(sample_clips, reps, threads=None):
-    """Times the oracle port (numpy restatement of the reference, oracle/gast_oracle.py) on the
-    host cores.  Needed-only (Optimized1f) schedule = the reference's fastest CPU form."""
-    import numpy as np
+    """Times the CPU port of the reference (oracle/gast_torch_ref.py: the same torch CPU kernels in
+    the same order as the reference modules -- bit-identical outputs, same cost) on all host
+    cores.  Needed-only (Optimized1f) schedule = the reference's fastest CPU form."""
+    import torch
     from oracle import gast_oracle as O
+    from oracle import gast_torch_ref as TR
     from gast_b200 import synth
-    from model.gast_net import SpatioTemporalModelOptimized1f
-    from common.skeleton import Skeleton
-    from common.graph_utils import adj_mx_from_skeleton
-    adj_t = adj_mx_from_skeleton(Skeleton(synth.skeleton_parents(J), [], []))
-    m = SpatioTemporalModelOptimized1f(adj_t, J, 2, J, FW, channels=CH)
-    synth.randomize_module(m, 1)
-    p = {k: v.numpy() for k, v in m.state_dict().items()}
-    adj = O.adj_from_parents(synth.skeleton_parents(J))
-    x = synth.synth_input(sample_clips, T, J, 2, seed=1234)
-    O.forward(x[:2], p, adj, FW, strided=True)      # warm
+    if threads:
+        torch.set_num_threads(threads)
+    else:
+        torch.set_num_threads(os.cpu_count())
+    if 'p' not in _CPU_STATE:
+        from model.gast_net import SpatioTemporalModelOptimized1f
+        from common.skeleton import Skeleton
+        from common.graph_utils import adj_mx_from_skeleton
+        adj_t = adj_mx_from_skeleton(Skeleton(synth.skeleton_parents(J), [], []))
+        m = SpatioTemporalModelOptimized1f(adj_t, J, 2, J, FW, channels=CH)
+        synth.randomize_module(m, 1)
+        _CPU_STATE['p'] = {k: v.clone() for k, v in m.state_dict().items()}
+        _CPU_STATE['masks'] = tuple(torch.from_numpy(a) for a in
+                                    O.local_masks(O.adj_from_parents(synth.skeleton_parents(J))))
+        with torch.no_grad():
+            TR.forward(torch.from_numpy(synth.synth_input(2, T, J, 2, seed=1)), _CPU_STATE['p'],
+                       _CPU_STATE['masks'], FW, strided=True)      # warm
+    x = torch.from_numpy(synth.synth_input(sample_clips, T, J, 2, seed=1234))
     ts = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        O.forward(x, p, adj, FW, strided=True)
-        ts.append(time.perf_counter() - t0)
-    cores = os.cpu_count()
-    try:
-        from threadpoolctl import threadpool_info
-        nt = [i.get('num_threads') for i in threadpool_info() if i.get('user_api') == 'blas']
-        if nt:
-            cores = max(nt)
-    except Exception:
-        pass
-    return sample_clips / statistics.median(ts), cores, ts
+    with torch.no_grad():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            TR.forward(x, _CPU_STATE['p'], _CPU_STATE['masks'], FW, strided=True)
+            ts.append(time.perf_counter() - t0)
+    return sample_clips / statistics.median(ts), torch.get_num_threads(), ts
 
 
 def run_reference(args, rank, world):
@@ -151,10 +157,12 @@ def run_reference(args, rank, world):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * sum(per_step) / len(per_step),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': '27f/17j/128ch GAST-Net forward, eval, fp32 (CPU port of the reference)',
-                   'clips_per_step': sample, 'frames': T, 'joints': J, 'channels': CH},
+        'config': {'workload': '27f/17j/128ch SpatioTemporalModel forward, eval, fp32 (BASELINE configs[1])',
+                   'clips_per_step': sample, 'frames': T, 'joints': J, 'channels': CH,
+                   'impl': 'CPU port of the reference on the host cores'},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': '%d clips per step, needed-only (Optimized1f) schedule, numpy/BLAS' % sample},
+                         'sample': '%d clips per step, needed-only (Optimized1f) schedule, torch-CPU port of the '
+                                   'reference (oracle/gast_torch_ref.py, bit-identical to it)' % sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -168,7 +176,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--clips', type=int, default=4096, help='clips per GPU per step')
-    ap.add_argument('--cpu-clips', type=int, default=16, help='clips per CPU-baseline sample')
+    ap.add_argument('--cpu-clips', type=int, default=64, help='clips per CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
 
@@ -293,10 +301,10 @@ def main():
                      'per_kernel_ms': prof['per_kernel_ms']},
     }
     if not args.no_cpu_baseline:
-        v, cores, ts = cpu_port_clips_per_s(args.cpu_clips, 3)
+        v, cores, ts = cpu_port_clips_per_s(args.cpu_clips, 5)
         line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                                'sample': '%d clips x 3 reps (median), needed-only schedule, numpy/BLAS port '
-                                          'of the reference (oracle/gast_oracle.py)' % args.cpu_clips}
+                                'sample': '%d clips x 5 reps (median), needed-only schedule, torch-CPU port of the '
+                                          'reference (oracle/gast_torch_ref.py)' % args.cpu_clips}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

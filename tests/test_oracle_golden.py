@@ -96,3 +96,39 @@ def test_full_equals_1f_and_sliding_window():
     for t in range(full.shape[1]):
         one = O.forward(x[:, t:t + 27], p, adj, m['filter_widths'], strided=True)
         assert np.abs(one[:, 0] - full[:, t]).max() < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# the torch-CPU restatement (oracle/gast_torch_ref.py): same goldens, incl. the large ones
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', SMALL_MODELS + CFG_MODELS)
+def test_torch_ref_forward(name):
+    import torch
+    from oracle import gast_torch_ref as TR
+    g = load_golden(name)
+    m = g['meta']
+    if name.startswith('cfg1') or name.startswith('cfg4_17_3333_c64_full'):
+        pytest.skip('large dilated case kept for the GPU path (CPU CI time)')
+    p = {k: torch.from_numpy(v) for k, v in params_from_meta(m).items()}
+    masks = tuple(torch.from_numpy(a) for a in O.local_masks(adj_for(m['J'])))
+    with torch.no_grad():
+        y = TR.forward(torch.from_numpy(g['x']), p, masks, m['filter_widths'], causal=m['causal'],
+                       strided=m['strided'], dense=m['dense']).numpy()
+    assert y.shape == g['y'].shape
+    assert np.abs(y - g['y']).max() < TOL
+
+
+def test_torch_ref_train_mode_matches_numpy_oracle_batch_stats():
+    """train-mode BN (batch statistics) agrees between the two restatements, dropout = 0."""
+    import torch
+    from oracle import gast_torch_ref as TR
+    g = load_golden('model_17_333_c16_1f_T27')
+    m = g['meta']
+    pn = params_from_meta(m)
+    adj = adj_for(17)
+    yn = O.forward(g['x'], pn, adj, m['filter_widths'], strided=True, training=True)
+    p = {k: torch.from_numpy(v) for k, v in pn.items()}
+    masks = tuple(torch.from_numpy(a) for a in O.local_masks(adj))
+    with torch.no_grad():
+        yt = TR.forward(torch.from_numpy(g['x']), p, masks, m['filter_widths'], strided=True, training=True).numpy()
+    assert np.abs(yn - yt).max() < 5e-5
