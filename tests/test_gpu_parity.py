@@ -194,3 +194,32 @@ def test_state_dict_roundtrip_and_inplace_output():
         y2[1, :, :, 0] *= -1
         y2[1, :, [4, 5, 6, 1, 2, 3]] = y2[1, :, [1, 2, 3, 4, 5, 6]]
         assert torch.mean(y2, dim=0, keepdim=True).shape == (1, 5, 17, 3)
+
+
+@pytest.mark.parametrize('J,fw,ch,B,T', [(17, [3, 3, 3], 128, 96, 27),        # BASELINE configs[1]/[2] shape
+                                         (17, [3, 3, 3, 3], 64, 40, 81),      # configs[3]: 81-frame model
+                                         (19, [3, 3, 3], 128, 75, 27),        # configs[4]: body+toe skeleton
+                                         (17, [3, 3, 3], 128, 3, 60)])        # whole-sequence (dilated) mode
+def test_baseline_configs_vs_torch_port(J, fw, ch, B, T, core):
+    """BASELINE.json configurations at full width against the torch-CPU port of the reference
+    (bit-identical to the reference modules), ragged batch sizes."""
+    from oracle import gast_torch_ref as TR
+    from oracle import gast_oracle as O
+    from model.gast_net import SpatioTemporalModel
+    m = SpatioTemporalModel(_adj(J), J, 2, J, fw, dropout=0.05, channels=ch)
+    synth.randomize_module(m, 21)
+    p = {k: v.clone() for k, v in m.state_dict().items()}
+    masks = tuple(torch.from_numpy(a) for a in O.local_masks(O.adj_from_parents(synth.skeleton_parents(J))))
+    x = torch.from_numpy(synth.synth_input(B, T, J, 2, seed=77))
+    n_ref = min(B, 24)
+    with torch.no_grad():
+        rf = 1 + 2 * sum(O.model_geometry(fw, False, False)[0])
+        ref = TR.forward(x[:n_ref], p, masks, fw, strided=(T == rf)).numpy()
+        y = m.cuda().eval()(x.cuda()).cpu().numpy()
+    assert y.shape[0] == B and y.shape[1:] == ref.shape[1:]
+    err = np.abs(y[:n_ref] - ref).max()
+    assert err < (TOL_FFMA if core == 1 else TOL), err
+    # MPJPE (common/loss.py:5-11) identical to 3 decimals in mm against a synthetic ground truth
+    gt = synth.synth_target(n_ref, J)[:, :, :, :] * np.ones((1, ref.shape[1], 1, 1), np.float32)
+    mp = lambda a: float(np.mean(np.linalg.norm(a.astype(np.float64) - gt, axis=-1)) * 1000.0)
+    assert round(mp(y[:n_ref]), 3) == round(mp(ref), 3), (mp(y[:n_ref]), mp(ref))
