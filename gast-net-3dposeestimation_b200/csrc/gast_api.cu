@@ -865,7 +865,18 @@ extern "C" int gast_debug_gemm(const float* A, const float* W, float* out, int32
     gemm_ffma_kernel<EPI_PLAIN><<<grid, FF_THREADS, ffma_smem_bytes(EPI_PLAIN, 1, 128, 1), st>>>(p);
     return (int)cudaGetLastError();
   };
+  unsigned long long* dbg = nullptr;
+  if (core == 0 && tc_mode == 6) {
+    // timing-attribution variant: counters land in `out` (M*N floats >= 148*32*2 required)
+    if ((size_t)M * N * sizeof(float) < 160 * 32 * sizeof(unsigned long long)) return fail("gast_debug_gemm: out too small for dbg");
+    dbg = reinterpret_cast<unsigned long long*>(out);
+    cudaMemsetAsync(dbg, 0, 160 * 32 * sizeof(unsigned long long), st);
+    p.dbg = dbg;
+    p.out = out + 160 * 32 * 2;      // results are garbage-tolerant in this mode; keep clear of the counters
+    p.F = M - 128;                   // stay inside the buffer
+  }
   rc = launch();
+  if (dbg) reps = 0;
   if (!rc && reps > 0) {
     cudaEventRecord(e0, st);
     for (int i = 0; i < reps && !rc; ++i) rc = launch();

@@ -66,8 +66,8 @@ struct GemmP {
   const float* bg;  // [N]
   int heads;
   int Cg;
-  // tcgen05 core numerics mode: 0 = 3xTF32 (product); 1 = hi.hi only (probe of the MMA's rounding)
-  int tc_mode;
+  int tc_mode;                 // unused by the product path
+  unsigned long long* dbg;     // DBG==6 timing variant of the tcgen05 kernel: per-CTA cycle counters
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) {

@@ -50,7 +50,9 @@ constexpr int TC_JMAX = 20;
 constexpr int TC_OFF_STAGING = TC_BSTAGES * TC_STAGE_BYTES;
 constexpr int TC_OFF_COEF = TC_OFF_STAGING + 128 * TC_SLD * 4;
 constexpr int TC_OFF_AB = TC_OFF_COEF + TC_MAX_NNZ * TC_SLD * 4;
-constexpr int TC_OFF_BAR = TC_OFF_AB + 128 * 8 * 4;
+constexpr int TC_XLD = 36;                            // transposition patch row stride (floats)
+constexpr int TC_OFF_XPOSE = TC_OFF_AB + 128 * 8 * 4;  // 4 warps x 32 rows x 36 floats
+constexpr int TC_OFF_BAR = TC_OFF_XPOSE + 4 * 32 * TC_XLD * 4;
 constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 256 + 1024;   // 12 mbarriers + tmem ptr   // + alignment slack
 
 // ----------------------------------------------------------------------------------------
@@ -166,6 +168,18 @@ __device__ __forceinline__ float tf32_rn_fast(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row atoms of 1024 B)
@@ -195,15 +209,19 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(T
 // kernel
 // ----------------------------------------------------------------------------------------
 // DBG != 0 builds timing-experiment variants (tools/tc_probe.py --perf): 1 = no TMEM->register
-// flush, 2 = no global A loads, 3 = main MMA only, 4 = no tcgen05.st of A, 5 = 1+2+4.
+// flush, 2 = no global A loads, 3 = main MMA only, 4 = no tcgen05.st of A, 5 = 1+2+4,
+// 6 = full kernel + clock64() attribution of every role's waits (written to p.dbg[blockIdx.x*32 + i]).
 template <int EPI, int DBG = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap map_lo, int n_tiles_n, int total_tiles) {
-  extern __shared__ unsigned char tc_smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  // No integer round-trip on this pointer: the compiler must keep knowing it is SHARED memory,
+  // otherwise every staging / transposition access becomes a generic LD/ST (ncu: 45 % of the
+  // A-producer samples were long-scoreboard stalls on generic loads from the patch).
+  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+  unsigned char* smem = tc_smem_raw;
   const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0) __trap();   // SWIZZLE_128B atoms need 1024-byte alignment
   float* staging = reinterpret_cast<float*>(smem + TC_OFF_STAGING);
   float* coef_s = reinterpret_cast<float*>(smem + TC_OFF_COEF);
   float* ab_s = reinterpret_cast<float*>(smem + TC_OFF_AB);
@@ -248,15 +266,19 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
   for (int s = 0; s < p.nseg; ++s) nchunks += p.seg[s].K / TC_BK;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 152;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     // ================================================================= A producers
-    // thread t owns tile row t (== TMEM lane t): it loads its 32-float slice of the K chunk
-    // (8 x LDG.128, 128 contiguous bytes along the channel axis), splits hi/lo and writes both to
-    // the A ring in tensor memory with tcgen05.st.
-    const int row = tid;
-    const int fr = row / J, jj = row - fr * J;
+    // Warp w owns tile rows 32w..32w+31 (== its TMEM lane quadrant).  Global loads are COALESCED:
+    // instruction i of a chunk covers rows 32w + 4i + (lane>>3), 8 lanes x 16 B = one 128-byte
+    // line per row along the channel axis (a row-per-thread mapping costs 32 L1 tag lookups per
+    // instruction and made the A path the bottleneck, profiles/r01_tc_attribution.md).  At hand-over
+    // the warp transposes the chunk through a private 32x36-float smem patch so that thread t
+    // holds row t, splits hi/lo and writes both into the A ring in tensor memory (tcgen05.st).
+    const int c16 = lane & 7;              // 16-byte chunk of the row
+    const int rsub = lane >> 3;            // row within the 4-row group of one instruction
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    long long roff = -1;
+    float* xpose = reinterpret_cast<float*>(smem + TC_OFF_XPOSE) + warp * (32 * TC_XLD);
+    long long roff[8];
     int c_tile = -1, c_seg = -1;
     auto ensure = [&](int tile, int sg) {
       if (tile == c_tile && sg == c_seg) return;
@@ -264,23 +286,29 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       const int f0 = (tile / n_tiles_n) * p.fpt;
       const int nf = min(p.fpt, p.F - f0);
       const RowMap mp = p.seg[sg].map;
-      if (fr < nf) {
-        int f = f0 + fr;
-        int b = f / mp.T_out;
-        int t = f - b * mp.T_out;
-        long long fin = (long long)b * mp.T_in + (long long)t * mp.t_mul + mp.t_off;
-        roff = (fin * J + jj) * (long long)p.seg[sg].ld;
-      } else {
-        roff = -1;
+      const long long ld = p.seg[sg].ld;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = warp * 32 + 4 * i + rsub;
+        const int fr_ = row / J, jj_ = row - fr_ * J;
+        if (fr_ < nf) {
+          int f = f0 + fr_;
+          int b = f / mp.T_out;
+          int t = f - b * mp.T_out;
+          long long fin = (long long)b * mp.T_in + (long long)t * mp.t_mul + mp.t_off;
+          roff[i] = (fin * J + jj_) * ld;
+        } else {
+          roff[i] = -1;
+        }
       }
     };
     auto load = [&](int sg, int k0, float4* v) {
       const ASeg& sgm = p.seg[sg];
       const int tap = k0 / sgm.Kc;
-      const float* src = sgm.base + tap * sgm.tap_stride + (k0 - tap * sgm.Kc) + roff;
+      const float* src = sgm.base + tap * sgm.tap_stride + (k0 - tap * sgm.Kc) + c16 * 4;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        v[i] = (roff >= 0 && DBG != 2 && DBG != 5) ? ldg4(src + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = (roff[i] >= 0 && DBG != 2 && DBG != 5) ? ldg4(src + roff[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     // Load cursor runs up to 3 chunks (48 KB per SM) ahead of the TMEM ring in REGISTERS: one
     // chunk per HBM round trip would leave the tensor pipe idle most of the time (ncu: long_sb
@@ -302,24 +330,37 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     int stage = 0;
     uint32_t phase = 0;
     bool running = true;
+    long long tA_wait = 0, tA_st = 0, tA_tot = clock64(), tA_n = 0;
     while (running) {
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
         if (!valid[s]) { running = false; break; }
+        // transpose: coalesced layout -> row per thread (stride 36 floats: conflict-free both ways)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(xpose + (4 * i + rsub) * TC_XLD + c16 * 4) = buf[s][i];
+        __syncwarp();
         uint32_t hi[32], lo[32];
         // hi = RN to tf32 (11 significant bits); lo = x - hi exactly.  lo is handed over
         // unrounded: the tensor core truncates it to tf32, an error <= 2^-21 |x| whose sign
         // is that of -lo, i.e. unbiased because hi was rounded to nearest.
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 x = buf[s][i];
+          const float4 x = *reinterpret_cast<const float4*>(xpose + lane * TC_XLD + i * 4);
           float h;
           h = tf32_rn_fast(x.x); hi[4 * i + 0] = __float_as_uint(h); lo[4 * i + 0] = __float_as_uint(x.x - h);
           h = tf32_rn_fast(x.y); hi[4 * i + 1] = __float_as_uint(h); lo[4 * i + 1] = __float_as_uint(x.y - h);
           h = tf32_rn_fast(x.z); hi[4 * i + 2] = __float_as_uint(h); lo[4 * i + 2] = __float_as_uint(x.z - h);
           h = tf32_rn_fast(x.w); hi[4 * i + 3] = __float_as_uint(h); lo[4 * i + 3] = __float_as_uint(x.w - h);
         }
+        __syncwarp();                      // patch free for the next chunk
+        // refill this register slot right away: the loads fly while we wait for the TMEM stage
+        valid[s] = have;
+        if (have) { ensure(tile, sg); load(sg, k0, buf[s]); advance(); }
+        long long t0 = 0;
+        if (DBG == 6) t0 = clock64();
         mbar_wait(bar0 + BA_EMPTY + 8 * stage, phase ^ 1);
+        if (DBG == 6) { long long t1 = clock64(); tA_wait += t1 - t0; t0 = t1; ++tA_n; }
         tc_fence_after();
         const uint32_t ta = tmem_base + lane_off + TC_A_COL + stage * 64;
         if (DBG != 4 && DBG != 5) {
@@ -330,10 +371,14 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar0 + BA_FULL + 8 * stage);
+        if (DBG == 6) tA_st += clock64() - t0;
         if (++stage == TC_ASTAGES) { stage = 0; phase ^= 1; }
-        valid[s] = have;
-        if (have) { ensure(tile, sg); load(sg, k0, buf[s]); advance(); }
       }
+    }
+    if (DBG == 6 && tid == 0 && p.dbg) {
+      unsigned long long* d = p.dbg + (size_t)blockIdx.x * 32;
+      d[0] = (unsigned long long)tA_n; d[1] = (unsigned long long)tA_wait; d[2] = (unsigned long long)tA_st;
+      d[3] = (unsigned long long)(clock64() - tA_tot);
     }
   } else if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -342,10 +387,14 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long tB_wait = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = (tile % n_tiles_n) * TC_BN;
         for (int c = 0; c < nchunks; ++c) {
+          long long t0 = 0;
+          if (DBG == 6) t0 = clock64();
           mbar_wait(bar0 + BB_EMPTY + 8 * stage, phase ^ 1);
+          if (DBG == 6) tB_wait += clock64() - t0;
           const uint32_t full = bar0 + BB_FULL + 8 * stage;
           mbar_arrive_expect_tx(full, 2 * 16384);
           const uint32_t dst = sbase + stage * TC_STAGE_BYTES;
@@ -354,52 +403,71 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           if (++stage == TC_BSTAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (DBG == 6 && p.dbg) p.dbg[(size_t)blockIdx.x * 32 + 8] = (unsigned long long)tB_wait;
     }
     __syncwarp();
     } else if (warp == 9) {
     // ================================================================= MMA issuer
-    if (lane == 0) {
+    // The whole warp runs this loop converged so that descriptors and barrier addresses live in
+    // uniform registers; one elected lane issues.  (Issuing from inside `if (lane == 0)` made
+    // every tcgen05.mma pay a ~55-cycle vector->uniform waterfall: 824 cycles per chunk for a
+    // 768-cycle MMA budget, profiles/r01_tc_attribution.md.)
+    {
       int bs = 0, as = 0;
       uint32_t bphase = 0, aphase = 0;
       uint32_t mcount = 0;                 // main buffers handed out so far
       uint32_t tphase = 0;                 // tile parity (corr buffer)
+      long long tM[5] = {0, 0, 0, 0, 0};
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(bar0 + BC_EMPTY, tphase ^ 1);  // corr buffer drained by the epilogue of the previous tile
         const uint32_t d_corr = tmem_base + CORR_COL;
         for (int c = 0; c < nchunks; ++c) {
           const uint32_t mb = mcount % NMAIN;
           const int cg = c % TC_FLUSH;                    // position in the flush group
+          long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+          if (DBG == 6) t0 = clock64();
           if (cg == 0) mbar_wait(bar0 + BM_EMPTY + 8 * mb, ((mcount / NMAIN) & 1) ^ 1);
+          if (DBG == 6) t1 = clock64();
           mbar_wait(bar0 + BA_FULL + 8 * as, aphase);
+          if (DBG == 6) t2 = clock64();
           mbar_wait(bar0 + BB_FULL + 8 * bs, bphase);
+          if (DBG == 6) t3 = clock64();
           tc_fence_after();
           const uint32_t d_main = tmem_base + mb * TC_BN;
           const uint32_t a_hi = tmem_base + TC_A_COL + as * 64, a_lo = a_hi + 32;
           const uint32_t sb = sbase + bs * TC_STAGE_BYTES;
           const uint64_t b_hi = make_smem_desc(sb), b_lo = make_smem_desc(sb + 16384);
+          const bool last_of_group = (cg == TC_FLUSH - 1 || c == nchunks - 1);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) {
-            const uint64_t adv = (uint64_t)(k * 2);      // 8 fp32 = 32 B = 2 x 16 B
-            umma_tf32_ts(d_main, a_hi + 8 * k, b_hi + adv, TC_IDESC, (cg | k) ? 1u : 0u);
-            if (DBG != 3) {
-              umma_tf32_ts(d_corr, a_lo + 8 * k, b_hi + adv, TC_IDESC, (c | k) ? 1u : 0u);
-              umma_tf32_ts(d_corr, a_hi + 8 * k, b_lo + adv, TC_IDESC, 1u);
+            for (int k = 0; k < TC_BK / 8; ++k) {
+              const uint64_t adv = (uint64_t)(k * 2);      // 8 fp32 = 32 B = 2 x 16 B
+              umma_tf32_ts(d_main, a_hi + 8 * k, b_hi + adv, TC_IDESC, (cg | k) ? 1u : 0u);
+              if (DBG != 3) {
+                umma_tf32_ts(d_corr, a_lo + 8 * k, b_hi + adv, TC_IDESC, (c | k) ? 1u : 0u);
+                umma_tf32_ts(d_corr, a_hi + 8 * k, b_lo + adv, TC_IDESC, 1u);
+              }
             }
+            umma_commit(bar0 + BB_EMPTY + 8 * bs);          // frees the B smem stage when the MMAs retire
+            umma_commit(bar0 + BA_EMPTY + 8 * as);          // frees the A tmem stage
+            if (last_of_group) umma_commit(bar0 + BM_FULL + 8 * mb);   // group sum ready
           }
-          umma_commit(bar0 + BB_EMPTY + 8 * bs);          // frees the B smem stage when the MMAs retire
-          umma_commit(bar0 + BA_EMPTY + 8 * as);          // frees the A tmem stage
-          if (cg == TC_FLUSH - 1 || c == nchunks - 1) {
-            umma_commit(bar0 + BM_FULL + 8 * mb);         // group sum ready
-            ++mcount;
-          }
+          __syncwarp();
+          if (last_of_group) ++mcount;
           if (++bs == TC_BSTAGES) { bs = 0; bphase ^= 1; }
           if (++as == TC_ASTAGES) { as = 0; aphase ^= 1; }
+          if (DBG == 6) {
+            const long long t4 = clock64();
+            tM[0] += 1; tM[1] += t1 - t0; tM[2] += t2 - t1; tM[3] += t3 - t2; tM[4] += t4 - t3;
+          }
         }
-        umma_commit(bar0 + BC_FULL);                      // correction term ready
+        if (elect_one()) umma_commit(bar0 + BC_FULL);       // correction term ready
+        __syncwarp();
         tphase ^= 1;
       }
+      if (DBG == 6 && p.dbg && lane == 0)
+        for (int i = 0; i < 5; ++i) p.dbg[(size_t)blockIdx.x * 32 + 16 + i] = (unsigned long long)tM[i];
     }
-    __syncwarp();
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
@@ -411,6 +479,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     const int fb = fr * J;                   // first row of this thread's frame
     uint32_t mcount = 0;
     uint32_t tphase = 0;
+    long long tE_n = 0, tE_wait = 0, tE_tot = clock64();
     const uint32_t lane_off = (uint32_t)(ew * 32) << 16;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int tn = tile % n_tiles_n;
@@ -449,7 +518,10 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       const int ngroups = (nchunks + TC_FLUSH - 1) / TC_FLUSH;
       for (int c = 0; c < ngroups; ++c) {
         const uint32_t mb = mcount % NMAIN;
+        long long t0 = 0;
+        if (DBG == 6) t0 = clock64();
         mbar_wait(bar0 + BM_FULL + 8 * mb, (mcount / NMAIN) & 1);
+        if (DBG == 6) { tE_n += 1; tE_wait += clock64() - t0; }
         tc_fence_after();
         const uint32_t taddr = tmem_base + mb * TC_BN + lane_off;
 #pragma unroll
@@ -622,6 +694,11 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         }
       }
     }
+    if (DBG == 6 && et == 0 && p.dbg) {
+      p.dbg[(size_t)blockIdx.x * 32 + 24] = (unsigned long long)tE_n;
+      p.dbg[(size_t)blockIdx.x * 32 + 25] = (unsigned long long)tE_wait;
+      p.dbg[(size_t)blockIdx.x * 32 + 26] = (unsigned long long)(clock64() - tE_tot);
+    }
   }
 
   tc_fence_before();
@@ -630,6 +707,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  (void)0;
 }
 
 // ----------------------------------------------------------------------------------------
@@ -748,6 +826,7 @@ inline int tc_launch(int sm_count, cudaStream_t st, int epi, const GemmP& p, con
       case 3: return tc_launch_dbg<3>(grid, st, p, t, nt, (int)total);
       case 4: return tc_launch_dbg<4>(grid, st, p, t, nt, (int)total);
       case 5: return tc_launch_dbg<5>(grid, st, p, t, nt, (int)total);
+      case 6: return tc_launch_dbg<6>(grid, st, p, t, nt, (int)total);
       default: return (int)cudaErrorInvalidValue;
     }
   }

@@ -51,6 +51,20 @@ def perf():
                                      torch.cuda.current_stream().cuda_stream)
             line += ' %s %.3f' % (name, ms.value) if rc == 0 else ' %s ERR(%s)' % (name, _lib.last_error()[:40])
         print(line, flush=True)
+        # clock64() attribution (DBG 6): cycles per chunk spent waiting, per role
+        ms = C.c_float(0)
+        rc = lib.gast_debug_gemm(a.data_ptr(), w.data_ptr(), o.data_ptr(), M, N, K, 0, 6, 0, C.byref(ms),
+                                 torch.cuda.current_stream().cuda_stream)
+        if rc == 0:
+            d = o.view(-1).view(torch.int64)[:148 * 32].reshape(148, 32).double().cpu().numpy()
+            nA = d[:, 0].mean(); nM = d[:, 16].mean(); nE = max(d[:, 24].mean(), 1)
+            print('   per chunk [cycles]: A-prod wait a_empty %.0f, store %.0f, loop total %.0f | B-prod wait b_empty %.0f |'
+                  ' MMA wait main_empty %.0f, a_full %.0f, b_full %.0f, issue+commit %.0f | epi wait main_full %.0f of %.0f per group'
+                  % (d[:, 1].mean() / nA, d[:, 2].mean() / nA, d[:, 3].mean() / nA, d[:, 8].mean() / nM,
+                     d[:, 17].mean() / nM, d[:, 18].mean() / nM, d[:, 19].mean() / nM, d[:, 20].mean() / nM,
+                     d[:, 25].mean() / nE, d[:, 26].mean() / nE), flush=True)
+        else:
+            print('   dbg6 failed:', _lib.last_error())
 
 
 def stats(name, D, ref):
