@@ -25,6 +25,7 @@
 // a 4th TMEM buffer that is added once per tile.
 #pragma once
 #include <cuda.h>
+#include <string.h>
 #include <vector>
 #include "gast_common.cuh"
 
@@ -41,7 +42,11 @@ struct TcWeights {
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;
 constexpr int TC_BSTAGES = 4;   // B (weights) ring in shared memory, filled by TMA
 constexpr int TC_ASTAGES = 2;
-constexpr int TC_FLUSH = 4;     // K chunks accumulated in TMEM before the sum is flushed to registers   // A (activations) ring in TENSOR MEMORY, filled by tcgen05.st
+constexpr int TC_FLUSH = 4;
+#ifndef GAST_TC_CLUSTER
+#define GAST_TC_CLUSTER 2
+#endif
+constexpr int TC_CLUSTER = GAST_TC_CLUSTER;   // CTAs per cluster: same N tile, adjacent M tiles, B multicast by TMA     // K chunks accumulated in TMEM before the sum is flushed to registers   // A (activations) ring in TENSOR MEMORY, filled by tcgen05.st
 constexpr int TC_THREADS = 384;   // 3 warpgroups: A producers | accumulate+epilogue | TMA, MMA, 2 idle
 constexpr int TC_STAGE_BYTES = 2 * 16384;            // B_hi, B_lo : 128 rows x 128 B each
 constexpr int TC_SLD = 68;                            // staging row stride (floats): conflict-free 16B rows
@@ -93,6 +98,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
 }
 
+// multicast form: the box lands at the same smem offset in every CTA of `mask`, and each of those
+// CTAs' mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -122,6 +146,12 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// arrive on the same barrier offset in every CTA of `mask` (frees a multicast-filled smem stage)
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
 
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (quadrant base + i).
@@ -215,6 +245,7 @@ template <int EPI, int DBG = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap map_lo, int n_tiles_n, int total_tiles) {
+  // total_tiles counts (M-tile group, N tile) work items: a group is TC_CLUSTER adjacent M tiles
   // No integer round-trip on this pointer: the compiler must keep knowing it is SHARED memory,
   // otherwise every staging / transposition access becomes a generic LD/ST (ncu: 45 % of the
   // A-producer samples were long-scoreboard stalls on generic loads from the patch).
@@ -238,11 +269,18 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const int J = p.J;
+  // Cluster of TC_CLUSTER CTAs: work item q = (group of adjacent M tiles, N tile); this CTA takes
+  // M tile TC_CLUSTER*(q / n_tiles_n) + rank.  An M tile beyond the last one is a dummy (all rows
+  // invalid) that still takes part in the B multicast protocol, so all CTAs of a cluster run the
+  // same number of chunks.
+  const uint32_t crank = (TC_CLUSTER > 1) ? cluster_ctarank() : 0u;
+  const int cid = blockIdx.x / TC_CLUSTER, ncl = gridDim.x / TC_CLUSTER;
+  auto tile_f0 = [&](int q) { return (TC_CLUSTER * (q / n_tiles_n) + (int)crank) * p.fpt; };
 
   if (tid == 0) {
     for (int s = 0; s < TC_BSTAGES; ++s) {
       mbar_init(bar0 + BB_FULL + 8 * s, 1);     // expect_tx arrive + TMA bytes
-      mbar_init(bar0 + BB_EMPTY + 8 * s, 1);    // tcgen05.commit
+      mbar_init(bar0 + BB_EMPTY + 8 * s, TC_CLUSTER);   // tcgen05.commit of every CTA of the cluster
     }
     for (int s = 0; s < TC_ASTAGES; ++s) {
       mbar_init(bar0 + BA_FULL + 8 * s, 4);     // 4 A-producer warps
@@ -259,6 +297,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
   if (warp == 9) tmem_alloc(sbase + TC_OFF_BAR + B_TMEMPTR, 512);
   tc_fence_before();
   __syncthreads();
+  if (TC_CLUSTER > 1) cluster_sync_all();   // peer barriers initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
@@ -279,22 +318,32 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     float* xpose = reinterpret_cast<float*>(smem + TC_OFF_XPOSE) + warp * (32 * TC_XLD);
     long long roff[8];
+    // (frame-in-tile, joint) of this thread's 8 rows, packed one byte each: fr*32 + jj
+    unsigned long long frjj = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = warp * 32 + 4 * i + rsub;
+      const int fr_ = row / J, jj_ = row - fr_ * J;
+      frjj |= (unsigned long long)((fr_ << 5) | jj_) << (8 * i);
+    }
     int c_tile = -1, c_seg = -1;
+    // row offsets of the current (tile, segment): ONE division per call, the frames of a tile
+    // are consecutive (the per-row divisions of the first version cost ~1000 cycles per call)
     auto ensure = [&](int tile, int sg) {
       if (tile == c_tile && sg == c_seg) return;
       c_tile = tile; c_seg = sg;
-      const int f0 = (tile / n_tiles_n) * p.fpt;
-      const int nf = min(p.fpt, p.F - f0);
+      const int f0 = tile_f0(tile);
+      const int nf = min(p.fpt, p.F - f0);          // <= 0 for a dummy tile
       const RowMap mp = p.seg[sg].map;
       const long long ld = p.seg[sg].ld;
+      const int b0 = f0 / mp.T_out, t0 = f0 - b0 * mp.T_out;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int row = warp * 32 + 4 * i + rsub;
-        const int fr_ = row / J, jj_ = row - fr_ * J;
+        const int code = (int)((frjj >> (8 * i)) & 0xff);
+        const int fr_ = code >> 5, jj_ = code & 31;
         if (fr_ < nf) {
-          int f = f0 + fr_;
-          int b = f / mp.T_out;
-          int t = f - b * mp.T_out;
+          int b = b0, t = t0 + fr_;
+          while (t >= mp.T_out) { t -= mp.T_out; ++b; }
           long long fin = (long long)b * mp.T_in + (long long)t * mp.t_mul + mp.t_off;
           roff[i] = (fin * J + jj_) * ld;
         } else {
@@ -313,11 +362,11 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     // Load cursor runs up to 3 chunks (48 KB per SM) ahead of the TMEM ring in REGISTERS: one
     // chunk per HBM round trip would leave the tensor pipe idle most of the time (ncu: long_sb
     // on the first use of the loaded tile, profiles/r01_tc_v1_*).
-    int tile = blockIdx.x, sg = 0, k0 = 0;
+    int tile = cid, sg = 0, k0 = 0;
     bool have = tile < total_tiles;
     auto advance = [&]() {
       k0 += TC_BK;
-      if (k0 >= p.seg[sg].K) { k0 = 0; ++sg; if (sg >= p.nseg) { sg = 0; tile += gridDim.x; } }
+      if (k0 >= p.seg[sg].K) { k0 = 0; ++sg; if (sg >= p.nseg) { sg = 0; tile += ncl; } }
       have = tile < total_tiles;
     };
     float4 buf[3][8];
@@ -330,16 +379,19 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     int stage = 0;
     uint32_t phase = 0;
     bool running = true;
-    long long tA_wait = 0, tA_st = 0, tA_tot = clock64(), tA_n = 0;
+    long long tA_wait = 0, tA_st = 0, tA_tot = clock64(), tA_n = 0, tA_ld = 0, tA_x = 0, tA_is = 0;
     while (running) {
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
         if (!valid[s]) { running = false; break; }
         // transpose: coalesced layout -> row per thread (stride 36 floats: conflict-free both ways)
+        long long tq0 = 0;
+        if (DBG == 6) tq0 = clock64();
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           *reinterpret_cast<float4*>(xpose + (4 * i + rsub) * TC_XLD + c16 * 4) = buf[s][i];
         __syncwarp();
+        if (DBG == 6) { long long tq1 = clock64(); tA_ld += tq1 - tq0; tq0 = tq1; }
         uint32_t hi[32], lo[32];
         // hi = RN to tf32 (11 significant bits); lo = x - hi exactly.  lo is handed over
         // unrounded: the tensor core truncates it to tf32, an error <= 2^-21 |x| whose sign
@@ -354,9 +406,11 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           h = tf32_rn_fast(x.w); hi[4 * i + 3] = __float_as_uint(h); lo[4 * i + 3] = __float_as_uint(x.w - h);
         }
         __syncwarp();                      // patch free for the next chunk
+        if (DBG == 6) { long long tq1 = clock64(); tA_x += tq1 - tq0; tq0 = tq1; }
         // refill this register slot right away: the loads fly while we wait for the TMEM stage
         valid[s] = have;
         if (have) { ensure(tile, sg); load(sg, k0, buf[s]); advance(); }
+        if (DBG == 6) tA_is += clock64() - tq0;
         long long t0 = 0;
         if (DBG == 6) t0 = clock64();
         mbar_wait(bar0 + BA_EMPTY + 8 * stage, phase ^ 1);
@@ -379,6 +433,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       unsigned long long* d = p.dbg + (size_t)blockIdx.x * 32;
       d[0] = (unsigned long long)tA_n; d[1] = (unsigned long long)tA_wait; d[2] = (unsigned long long)tA_st;
       d[3] = (unsigned long long)(clock64() - tA_tot);
+      d[4] = (unsigned long long)tA_ld; d[5] = (unsigned long long)tA_x; d[6] = (unsigned long long)tA_is;
     }
   } else if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -388,18 +443,29 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       int stage = 0;
       uint32_t phase = 0;
       long long tB_wait = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = cid; tile < total_tiles; tile += ncl) {
         const int n0 = (tile % n_tiles_n) * TC_BN;
         for (int c = 0; c < nchunks; ++c) {
           long long t0 = 0;
           if (DBG == 6) t0 = clock64();
-          mbar_wait(bar0 + BB_EMPTY + 8 * stage, phase ^ 1);
+          mbar_wait(bar0 + BB_EMPTY + 8 * stage, phase ^ 1);     // every CTA of the cluster consumed it
           if (DBG == 6) tB_wait += clock64() - t0;
           const uint32_t full = bar0 + BB_FULL + 8 * stage;
-          mbar_arrive_expect_tx(full, 2 * 16384);
-          const uint32_t dst = sbase + stage * TC_STAGE_BYTES;
-          tma_load_2d(dst, &map_hi, full, c * TC_BK, n0);
-          tma_load_2d(dst + 16384, &map_lo, full, c * TC_BK, n0);
+          mbar_arrive_expect_tx(full, 2 * 16384);                // own share + the peers' shares
+          if (TC_CLUSTER > 1) {
+            // this CTA fetches rows [R*rank, R*rank+R) of the 128-row B tile (hi and lo) and
+            // multicasts them into every CTA of the cluster: each weight byte crosses the L2->SM
+            // fabric once per cluster instead of once per CTA
+            constexpr int R = TC_BN / TC_CLUSTER;
+            const uint32_t dst = sbase + stage * TC_STAGE_BYTES + crank * (R * 128);
+            const uint16_t mask = (uint16_t)((1u << TC_CLUSTER) - 1);
+            tma_load_2d_mc(dst, &map_hi, full, c * TC_BK, n0 + R * (int)crank, mask);
+            tma_load_2d_mc(dst + 16384, &map_lo, full, c * TC_BK, n0 + R * (int)crank, mask);
+          } else {
+            const uint32_t dst = sbase + stage * TC_STAGE_BYTES;
+            tma_load_2d(dst, &map_hi, full, c * TC_BK, n0);
+            tma_load_2d(dst + 16384, &map_lo, full, c * TC_BK, n0);
+          }
           if (++stage == TC_BSTAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -418,7 +484,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       uint32_t mcount = 0;                 // main buffers handed out so far
       uint32_t tphase = 0;                 // tile parity (corr buffer)
       long long tM[5] = {0, 0, 0, 0, 0};
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = cid; tile < total_tiles; tile += ncl) {
         mbar_wait(bar0 + BC_EMPTY, tphase ^ 1);  // corr buffer drained by the epilogue of the previous tile
         const uint32_t d_corr = tmem_base + CORR_COL;
         for (int c = 0; c < nchunks; ++c) {
@@ -448,7 +514,8 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
                 umma_tf32_ts(d_corr, a_hi + 8 * k, b_lo + adv, TC_IDESC, 1u);
               }
             }
-            umma_commit(bar0 + BB_EMPTY + 8 * bs);          // frees the B smem stage when the MMAs retire
+            if (TC_CLUSTER > 1) umma_commit_mc(bar0 + BB_EMPTY + 8 * bs, (uint16_t)((1u << TC_CLUSTER) - 1));
+            else umma_commit(bar0 + BB_EMPTY + 8 * bs);     // frees the B smem stage when the MMAs retire
             umma_commit(bar0 + BA_EMPTY + 8 * as);          // frees the A tmem stage
             if (last_of_group) umma_commit(bar0 + BM_FULL + 8 * mb);   // group sum ready
           }
@@ -481,10 +548,10 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     uint32_t tphase = 0;
     long long tE_n = 0, tE_wait = 0, tE_tot = clock64();
     const uint32_t lane_off = (uint32_t)(ew * 32) << 16;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = cid; tile < total_tiles; tile += ncl) {
       const int tn = tile % n_tiles_n;
-      const int f0 = (tile / n_tiles_n) * p.fpt;
-      const int nf = min(p.fpt, p.F - f0);
+      const int f0 = tile_f0(tile);
+      const int nf = max(0, min(p.fpt, p.F - f0));
       const int vrows = nf * J;
       const int n0 = tn * TC_BN;
       const bool valid = r < vrows;
@@ -703,6 +770,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
 
   tc_fence_before();
   __syncthreads();
+  if (TC_CLUSTER > 1) cluster_sync_all();   // peers may multicast into / arrive on this CTA until they finish
   if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -770,7 +838,7 @@ inline int tc_prepare_weights(TcWeights& t, const float* W, int N, int K, cudaSt
     t.hi = (float*)a; t.lo = (float*)b; t.N = N; t.K = K;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
     cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BN};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)(TC_BN / TC_CLUSTER)};   // each CTA fetches its share
     cuuint32_t estr[2] = {1, 1};
     CUresult r1 = enc(&t.map_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, t.hi, dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -803,46 +871,53 @@ inline bool tc_supported(const GemmP& p, int epi, const TcWeights& t) {
   return true;
 }
 
-template <int DBG>
-inline int tc_launch_dbg(int grid, cudaStream_t st, const GemmP& p, const TcWeights& t, int nt, int total) {
-  cudaError_t e = cudaFuncSetAttribute((const void*)gemm_tc_kernel<EPI_PLAIN, DBG>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (e != cudaSuccess) return (int)e;
-  gemm_tc_kernel<EPI_PLAIN, DBG><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p, t.map_hi, t.map_lo, nt, total);
-  return (int)cudaGetLastError();
+template <int EPI, int DBG>
+inline int tc_launch_one(int grid, cudaStream_t st, const GemmP& p, const TcWeights& t, int nt, int items) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)gemm_tc_kernel<EPI, DBG>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = TC_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, DBG>, p, t.map_hi, t.map_lo, nt, items);
 }
 
 inline int tc_launch(int sm_count, cudaStream_t st, int epi, const GemmP& p, const TcWeights& t, int dbg = 0) {
   const int mt = (p.F + p.fpt - 1) / p.fpt;
   const int nt = (p.N + TC_BN - 1) / TC_BN;
-  const long long total = (long long)mt * nt;
-  if (total > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
-  const int grid = (int)(total < sm_count ? total : sm_count);
+  const long long items = (long long)((mt + TC_CLUSTER - 1) / TC_CLUSTER) * nt;
+  if (items > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+  const int max_cl = sm_count / TC_CLUSTER;
+  const int grid = TC_CLUSTER * (int)(items < max_cl ? items : max_cl);
   if (dbg) {
     if (epi != EPI_PLAIN) return (int)cudaErrorInvalidValue;
     switch (dbg) {
-      case 1: return tc_launch_dbg<1>(grid, st, p, t, nt, (int)total);
-      case 2: return tc_launch_dbg<2>(grid, st, p, t, nt, (int)total);
-      case 3: return tc_launch_dbg<3>(grid, st, p, t, nt, (int)total);
-      case 4: return tc_launch_dbg<4>(grid, st, p, t, nt, (int)total);
-      case 5: return tc_launch_dbg<5>(grid, st, p, t, nt, (int)total);
-      case 6: return tc_launch_dbg<6>(grid, st, p, t, nt, (int)total);
+      case 1: return tc_launch_one<EPI_PLAIN, 1>(grid, st, p, t, nt, (int)items);
+      case 2: return tc_launch_one<EPI_PLAIN, 2>(grid, st, p, t, nt, (int)items);
+      case 3: return tc_launch_one<EPI_PLAIN, 3>(grid, st, p, t, nt, (int)items);
+      case 4: return tc_launch_one<EPI_PLAIN, 4>(grid, st, p, t, nt, (int)items);
+      case 5: return tc_launch_one<EPI_PLAIN, 5>(grid, st, p, t, nt, (int)items);
+      case 6: return tc_launch_one<EPI_PLAIN, 6>(grid, st, p, t, nt, (int)items);
       default: return (int)cudaErrorInvalidValue;
     }
   }
-  static bool attr_set[3] = {false, false, false};
-  const void* fn = epi == EPI_PLAIN ? (const void*)gemm_tc_kernel<EPI_PLAIN, 0>
-                 : epi == EPI_SEMCH ? (const void*)gemm_tc_kernel<EPI_SEMCH, 0>
-                                    : (const void*)gemm_tc_kernel<EPI_GLOBAL, 0>;
-  if (!attr_set[epi]) {
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    attr_set[epi] = true;
-  }
-  if (epi == EPI_PLAIN) gemm_tc_kernel<EPI_PLAIN, 0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p, t.map_hi, t.map_lo, nt, (int)total);
-  else if (epi == EPI_SEMCH) gemm_tc_kernel<EPI_SEMCH, 0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p, t.map_hi, t.map_lo, nt, (int)total);
-  else gemm_tc_kernel<EPI_GLOBAL, 0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p, t.map_hi, t.map_lo, nt, (int)total);
-  return (int)cudaGetLastError();
+  if (epi == EPI_PLAIN) return tc_launch_one<EPI_PLAIN, 0>(grid, st, p, t, nt, (int)items);
+  if (epi == EPI_SEMCH) return tc_launch_one<EPI_SEMCH, 0>(grid, st, p, t, nt, (int)items);
+  return tc_launch_one<EPI_GLOBAL, 0>(grid, st, p, t, nt, (int)items);
 }
 
 }  // namespace gast

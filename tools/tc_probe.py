@@ -58,9 +58,9 @@ def perf():
         if rc == 0:
             d = o.view(-1).view(torch.int64)[:148 * 32].reshape(148, 32).double().cpu().numpy()
             nA = d[:, 0].mean(); nM = d[:, 16].mean(); nE = max(d[:, 24].mean(), 1)
-            print('   per chunk [cycles]: A-prod wait a_empty %.0f, store %.0f, loop total %.0f | B-prod wait b_empty %.0f |'
+            print('   per chunk [cycles]: A-prod global-data wait+STS %.0f, LDS+split %.0f, refill issue %.0f, wait a_empty %.0f, STTM+arrive %.0f, loop total %.0f | B-prod wait b_empty %.0f |'
                   ' MMA wait main_empty %.0f, a_full %.0f, b_full %.0f, issue+commit %.0f | epi wait main_full %.0f of %.0f per group'
-                  % (d[:, 1].mean() / nA, d[:, 2].mean() / nA, d[:, 3].mean() / nA, d[:, 8].mean() / nM,
+                  % (d[:, 4].mean() / nA, d[:, 5].mean() / nA, d[:, 6].mean() / nA, d[:, 1].mean() / nA, d[:, 2].mean() / nA, d[:, 3].mean() / nA, d[:, 8].mean() / nM,
                      d[:, 17].mean() / nM, d[:, 18].mean() / nM, d[:, 19].mean() / nM, d[:, 20].mean() / nM,
                      d[:, 25].mean() / nE, d[:, 26].mean() / nE), flush=True)
         else:
