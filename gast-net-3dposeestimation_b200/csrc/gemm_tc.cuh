@@ -40,7 +40,8 @@ struct TcWeights {
 };
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;
-constexpr int TC_BSTAGES = 4;   // B (weights) ring in shared memory, filled by TMA
+constexpr int TC_BSTAGES = 3;   // B (weights) ring in shared memory, filled by TMA
+constexpr int TC_RSTAGES = 4;   // raw A ring in shared memory, filled by cp.async (no register staging, no MSHR cap)
 constexpr int TC_ASTAGES = 2;
 constexpr int TC_FLUSH = 4;
 #ifndef GAST_TC_CLUSTER
@@ -55,9 +56,9 @@ constexpr int TC_JMAX = 20;
 constexpr int TC_OFF_STAGING = TC_BSTAGES * TC_STAGE_BYTES;
 constexpr int TC_OFF_COEF = TC_OFF_STAGING + 128 * TC_SLD * 4;
 constexpr int TC_OFF_AB = TC_OFF_COEF + TC_MAX_NNZ * TC_SLD * 4;
-constexpr int TC_XLD = 36;                            // transposition patch row stride (floats)
-constexpr int TC_OFF_XPOSE = TC_OFF_AB + 128 * 8 * 4;  // 4 warps x 32 rows x 36 floats
-constexpr int TC_OFF_BAR = TC_OFF_XPOSE + 4 * 32 * TC_XLD * 4;
+constexpr int TC_XLD = 36;                            // raw A row stride (floats): conflict-free row-per-thread reads
+constexpr int TC_OFF_XPOSE = TC_OFF_AB + 128 * 8 * 4;  // raw A ring: TC_RSTAGES x 128 rows x 36 floats
+constexpr int TC_OFF_BAR = TC_OFF_XPOSE + TC_RSTAGES * 128 * TC_XLD * 4;
 constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 256 + 1024;   // 12 mbarriers + tmem ptr   // + alignment slack
 
 // ----------------------------------------------------------------------------------------
@@ -198,6 +199,14 @@ __device__ __forceinline__ float tf32_rn_fast(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
+// 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 writes zeros
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // one lane of the (converged) warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -305,7 +314,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
   for (int s = 0; s < p.nseg; ++s) nchunks += p.seg[s].K / TC_BK;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 152;");
     // ================================================================= A producers
     // Warp w owns tile rows 32w..32w+31 (== its TMEM lane quadrant).  Global loads are COALESCED:
     // instruction i of a chunk covers rows 32w + 4i + (lane>>3), 8 lanes x 16 B = one 128-byte
@@ -351,17 +360,24 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         }
       }
     };
-    auto load = [&](int sg, int k0, float4* v) {
+    // Raw A goes global -> shared with cp.async (LDGSTS): no register staging and, unlike LDG, no
+    // cap on the bytes in flight (with a register ring the LSU accepted ~16 KB per SM and the
+    // refill of 8 LDG.128 took ~750 cycles of issue stalls, profiles/r01_tc_attribution.md).
+    // Slot r of the ring holds this warp's 32 rows x 32 floats at a 36-float stride.
+    const uint32_t raw0 = sbase + TC_OFF_XPOSE + (uint32_t)(warp * 32 * TC_XLD * 4);
+    auto issue = [&](int sg, int k0, int slot) {
       const ASeg& sgm = p.seg[sg];
       const int tap = k0 / sgm.Kc;
       const float* src = sgm.base + tap * sgm.tap_stride + (k0 - tap * sgm.Kc) + c16 * 4;
+      const uint32_t dst = raw0 + (uint32_t)(slot * 128 * TC_XLD * 4) + (uint32_t)(rsub * TC_XLD * 4 + c16 * 16);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        v[i] = (roff[i] >= 0 && DBG != 2 && DBG != 5) ? ldg4(src + roff[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 8; ++i) {
+        const bool ok = roff[i] >= 0 && DBG != 2 && DBG != 5;
+        cp_async16(dst + (uint32_t)(4 * i * TC_XLD * 4), ok ? (const void*)(src + roff[i]) : (const void*)sgm.base,
+                   ok ? 16u : 0u);
+      }
+      cp_async_commit();
     };
-    // Load cursor runs up to 3 chunks (48 KB per SM) ahead of the TMEM ring in REGISTERS: one
-    // chunk per HBM round trip would leave the tensor pipe idle most of the time (ncu: long_sb
-    // on the first use of the loaded tile, profiles/r01_tc_v1_*).
     int tile = cid, sg = 0, k0 = 0;
     bool have = tile < total_tiles;
     auto advance = [&]() {
@@ -369,66 +385,63 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       if (k0 >= p.seg[sg].K) { k0 = 0; ++sg; if (sg >= p.nseg) { sg = 0; tile += ncl; } }
       have = tile < total_tiles;
     };
-    float4 buf[3][8];
-    bool valid[3];
-#pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      valid[s] = have;
-      if (have) { ensure(tile, sg); load(sg, k0, buf[s]); advance(); }
+    // my chunk count (same iteration space as the other roles)
+    long long my_chunks = 0;
+    for (int q = cid; q < total_tiles; q += ncl) my_chunks += nchunks;
+    // prologue: fill the ring
+    int issued = 0;
+    for (int r = 0; r < TC_RSTAGES; ++r) {
+      if (have) { ensure(tile, sg); issue(sg, k0, r); advance(); ++issued; }
+      else cp_async_commit();               // keep group accounting uniform
     }
-    int stage = 0;
+    int stage = 0, slot = 0;
     uint32_t phase = 0;
-    bool running = true;
     long long tA_wait = 0, tA_st = 0, tA_tot = clock64(), tA_n = 0, tA_ld = 0, tA_x = 0, tA_is = 0;
-    while (running) {
+    for (long long c = 0; c < my_chunks; ++c) {
+      long long tq0 = 0;
+      if (DBG == 6) tq0 = clock64();
+      cp_async_wait<TC_RSTAGES - 1>();      // the oldest group (this chunk) has landed
+      __syncwarp();
+      if (DBG == 6) { long long tq1 = clock64(); tA_ld += tq1 - tq0; tq0 = tq1; }
+      uint32_t hi[32], lo[32];
+      // hi = RN to tf32 (11 significant bits); lo = x - hi exactly.  lo is handed over
+      // unrounded: the tensor core truncates it to tf32, an error <= 2^-21 |x| whose sign
+      // is that of -lo, i.e. unbiased because hi was rounded to nearest.
+      const float* rowp = reinterpret_cast<const float*>(smem + TC_OFF_XPOSE) +
+                          (size_t)slot * 128 * TC_XLD + (size_t)(warp * 32 + lane) * TC_XLD;
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        if (!valid[s]) { running = false; break; }
-        // transpose: coalesced layout -> row per thread (stride 36 floats: conflict-free both ways)
-        long long tq0 = 0;
-        if (DBG == 6) tq0 = clock64();
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<float4*>(xpose + (4 * i + rsub) * TC_XLD + c16 * 4) = buf[s][i];
-        __syncwarp();
-        if (DBG == 6) { long long tq1 = clock64(); tA_ld += tq1 - tq0; tq0 = tq1; }
-        uint32_t hi[32], lo[32];
-        // hi = RN to tf32 (11 significant bits); lo = x - hi exactly.  lo is handed over
-        // unrounded: the tensor core truncates it to tf32, an error <= 2^-21 |x| whose sign
-        // is that of -lo, i.e. unbiased because hi was rounded to nearest.
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 x = *reinterpret_cast<const float4*>(xpose + lane * TC_XLD + i * 4);
-          float h;
-          h = tf32_rn_fast(x.x); hi[4 * i + 0] = __float_as_uint(h); lo[4 * i + 0] = __float_as_uint(x.x - h);
-          h = tf32_rn_fast(x.y); hi[4 * i + 1] = __float_as_uint(h); lo[4 * i + 1] = __float_as_uint(x.y - h);
-          h = tf32_rn_fast(x.z); hi[4 * i + 2] = __float_as_uint(h); lo[4 * i + 2] = __float_as_uint(x.z - h);
-          h = tf32_rn_fast(x.w); hi[4 * i + 3] = __float_as_uint(h); lo[4 * i + 3] = __float_as_uint(x.w - h);
-        }
-        __syncwarp();                      // patch free for the next chunk
-        if (DBG == 6) { long long tq1 = clock64(); tA_x += tq1 - tq0; tq0 = tq1; }
-        // refill this register slot right away: the loads fly while we wait for the TMEM stage
-        valid[s] = have;
-        if (have) { ensure(tile, sg); load(sg, k0, buf[s]); advance(); }
-        if (DBG == 6) tA_is += clock64() - tq0;
-        long long t0 = 0;
-        if (DBG == 6) t0 = clock64();
-        mbar_wait(bar0 + BA_EMPTY + 8 * stage, phase ^ 1);
-        if (DBG == 6) { long long t1 = clock64(); tA_wait += t1 - t0; t0 = t1; ++tA_n; }
-        tc_fence_after();
-        const uint32_t ta = tmem_base + lane_off + TC_A_COL + stage * 64;
-        if (DBG != 4 && DBG != 5) {
-          tmem_st32(ta, hi);
-          tmem_st32(ta + 32, lo);
-          tmem_wait_st();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar0 + BA_FULL + 8 * stage);
-        if (DBG == 6) tA_st += clock64() - t0;
-        if (++stage == TC_ASTAGES) { stage = 0; phase ^= 1; }
+      for (int i = 0; i < 8; ++i) {
+        const float4 x = *reinterpret_cast<const float4*>(rowp + i * 4);
+        float h;
+        h = tf32_rn_fast(x.x); hi[4 * i + 0] = __float_as_uint(h); lo[4 * i + 0] = __float_as_uint(x.x - h);
+        h = tf32_rn_fast(x.y); hi[4 * i + 1] = __float_as_uint(h); lo[4 * i + 1] = __float_as_uint(x.y - h);
+        h = tf32_rn_fast(x.z); hi[4 * i + 2] = __float_as_uint(h); lo[4 * i + 2] = __float_as_uint(x.z - h);
+        h = tf32_rn_fast(x.w); hi[4 * i + 3] = __float_as_uint(h); lo[4 * i + 3] = __float_as_uint(x.w - h);
       }
+      __syncwarp();                         // slot free: refill it right away
+      if (DBG == 6) { long long tq1 = clock64(); tA_x += tq1 - tq0; tq0 = tq1; }
+      if (have) { ensure(tile, sg); issue(sg, k0, slot); advance(); }
+      else cp_async_commit();
+      if (DBG == 6) tA_is += clock64() - tq0;
+      long long t0 = 0;
+      if (DBG == 6) t0 = clock64();
+      mbar_wait(bar0 + BA_EMPTY + 8 * stage, phase ^ 1);
+      if (DBG == 6) { long long t1 = clock64(); tA_wait += t1 - t0; t0 = t1; ++tA_n; }
+      tc_fence_after();
+      const uint32_t ta = tmem_base + lane_off + TC_A_COL + stage * 64;
+      if (DBG != 4 && DBG != 5) {
+        tmem_st32(ta, hi);
+        tmem_st32(ta + 32, lo);
+        tmem_wait_st();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + BA_FULL + 8 * stage);
+      if (DBG == 6) tA_st += clock64() - t0;
+      if (++stage == TC_ASTAGES) { stage = 0; phase ^= 1; }
+      if (++slot == TC_RSTAGES) slot = 0;
     }
+    cp_async_wait<0>();
     if (DBG == 6 && tid == 0 && p.dbg) {
       unsigned long long* d = p.dbg + (size_t)blockIdx.x * 32;
       d[0] = (unsigned long long)tA_n; d[1] = (unsigned long long)tA_wait; d[2] = (unsigned long long)tA_st;
