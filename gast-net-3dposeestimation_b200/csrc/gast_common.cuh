@@ -67,6 +67,9 @@ struct GemmP {
   int heads;
   int Cg;
   int tc_mode;                 // unused by the product path
+  // tcgen05 core, A operand by TMA (set by tc_launch when every segment's frame map is affine):
+  int a_tma;                   // 1 = raw A tiles arrive by cp.async.bulk.tensor.3d, 0 = cp.async gather
+  int a_map0[3];               // first tensor-map index of each segment (one map per temporal tap)
   unsigned long long* dbg;     // DBG==6 timing variant of the tcgen05 kernel: per-CTA cycle counters
 };
 

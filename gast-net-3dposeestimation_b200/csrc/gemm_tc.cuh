@@ -99,6 +99,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
 // multicast form: the box lands at the same smem offset in every CTA of `mask`, and each of those
 // CTAs' mbarrier (same offset) receives the complete_tx
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y,
@@ -253,7 +259,9 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(T
 template <int EPI, int DBG = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensorMap map_hi,
-               const __grid_constant__ CUtensorMap map_lo, int n_tiles_n, int total_tiles) {
+               const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap amap0,
+               const __grid_constant__ CUtensorMap amap1, const __grid_constant__ CUtensorMap amap2,
+               int n_tiles_n, int total_tiles) {
   // total_tiles counts (M-tile group, N tile) work items: a group is TC_CLUSTER adjacent M tiles
   // No integer round-trip on this pointer: the compiler must keep knowing it is SHARED memory,
   // otherwise every staging / transposition access becomes a generic LD/ST (ncu: 45 % of the
@@ -269,7 +277,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
   // mbarriers (8 B each):  b_full[4] @0  b_empty[4] @32  a_full[2] @64  a_empty[2] @80
   //                        main_full[2] @96  main_empty[2] @112  corr_full @128  corr_empty @136 ; tmem ptr @144
   constexpr uint32_t BB_FULL = 0, BB_EMPTY = 32, BA_FULL = 64, BA_EMPTY = 80, BM_FULL = 96, BM_EMPTY = 112,
-                     BC_FULL = 128, BC_EMPTY = 136, B_TMEMPTR = 144;
+                     BC_FULL = 128, BC_EMPTY = 136, B_TMEMPTR = 144, BR_FULL = 160, BR_EMPTY = 192;
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + TC_OFF_BAR + B_TMEMPTR);
   constexpr uint32_t NMAIN = TC_NMAIN;
   constexpr uint32_t CORR_COL = TC_CORR_COL;
@@ -298,6 +306,10 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     for (int b = 0; b < (int)NMAIN; ++b) {
       mbar_init(bar0 + BM_FULL + 8 * b, 1);     // tcgen05.commit
       mbar_init(bar0 + BM_EMPTY + 8 * b, 4);    // 4 accumulate/epilogue warps
+    }
+    for (int r = 0; r < TC_RSTAGES; ++r) {
+      mbar_init(bar0 + BR_FULL + 8 * r, 1);     // raw A slot: expect_tx arrive + TMA bytes
+      mbar_init(bar0 + BR_EMPTY + 8 * r, 4);    // 4 A-producer warps have read it
     }
     mbar_init(bar0 + BC_FULL, 1);
     mbar_init(bar0 + BC_EMPTY, 4);
@@ -360,16 +372,22 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         }
       }
     };
-    // Raw A goes global -> shared with cp.async (LDGSTS): no register staging and, unlike LDG, no
-    // cap on the bytes in flight (with a register ring the LSU accepted ~16 KB per SM and the
-    // refill of 8 LDG.128 took ~750 cycles of issue stalls, profiles/r01_tc_attribution.md).
-    // Slot r of the ring holds this warp's 32 rows x 32 floats at a 36-float stride.
+    long long my_chunks = 0;
+    for (int q = cid; q < total_tiles; q += ncl) my_chunks += nchunks;
+    int stage = 0, slot = 0;
+    uint32_t phase = 0, rphase = 0;
+    long long tA_wait = 0, tA_st = 0, tA_tot = clock64(), tA_n = 0, tA_ld = 0, tA_x = 0, tA_is = 0;
+    // Raw A reaches shared memory either by TMA (affine frame maps: warp 10 issues one
+    // cp.async.bulk.tensor.3d per chunk, 128-byte-swizzled rows) or by a cp.async gather issued
+    // here (general frame maps: dilated stages on long sequences, dense ablation).  Either way it
+    // never passes through registers on its way in: the LSU path caps the bytes in flight per SM
+    // (profiles/r01_tc_attribution.md), TMA does not.
     const uint32_t raw0 = sbase + TC_OFF_XPOSE + (uint32_t)(warp * 32 * TC_XLD * 4);
-    auto issue = [&](int sg, int k0, int slot) {
+    auto issue = [&](int sg, int k0, int slot_) {
       const ASeg& sgm = p.seg[sg];
       const int tap = k0 / sgm.Kc;
       const float* src = sgm.base + tap * sgm.tap_stride + (k0 - tap * sgm.Kc) + c16 * 4;
-      const uint32_t dst = raw0 + (uint32_t)(slot * 128 * TC_XLD * 4) + (uint32_t)(rsub * TC_XLD * 4 + c16 * 16);
+      const uint32_t dst = raw0 + (uint32_t)(slot_ * 128 * TC_XLD * 4) + (uint32_t)(rsub * TC_XLD * 4 + c16 * 16);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const bool ok = roff[i] >= 0 && DBG != 2 && DBG != 5;
@@ -385,43 +403,51 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       if (k0 >= p.seg[sg].K) { k0 = 0; ++sg; if (sg >= p.nseg) { sg = 0; tile += ncl; } }
       have = tile < total_tiles;
     };
-    // my chunk count (same iteration space as the other roles)
-    long long my_chunks = 0;
-    for (int q = cid; q < total_tiles; q += ncl) my_chunks += nchunks;
-    // prologue: fill the ring
-    int issued = 0;
-    for (int r = 0; r < TC_RSTAGES; ++r) {
-      if (have) { ensure(tile, sg); issue(sg, k0, r); advance(); ++issued; }
-      else cp_async_commit();               // keep group accounting uniform
+    const bool atma = p.a_tma != 0;
+    if (!atma) {
+      for (int r = 0; r < TC_RSTAGES; ++r) {   // prologue: fill the ring
+        if (have) { ensure(tile, sg); issue(sg, k0, r); advance(); }
+        else cp_async_commit();               // keep group accounting uniform
+      }
     }
-    int stage = 0, slot = 0;
-    uint32_t phase = 0;
-    long long tA_wait = 0, tA_st = 0, tA_tot = clock64(), tA_n = 0, tA_ld = 0, tA_x = 0, tA_is = 0;
+    const int my_row = warp * 32 + lane;
+    const bool row_in_box = my_row < p.fpt * J;
     for (long long c = 0; c < my_chunks; ++c) {
       long long tq0 = 0;
       if (DBG == 6) tq0 = clock64();
-      cp_async_wait<TC_RSTAGES - 1>();      // the oldest group (this chunk) has landed
-      __syncwarp();
+      if (atma) {
+        mbar_wait(bar0 + BR_FULL + 8 * slot, rphase);
+      } else {
+        cp_async_wait<TC_RSTAGES - 1>();      // the oldest group (this chunk) has landed
+        __syncwarp();
+      }
       if (DBG == 6) { long long tq1 = clock64(); tA_ld += tq1 - tq0; tq0 = tq1; }
       uint32_t hi[32], lo[32];
       // hi = RN to tf32 (11 significant bits); lo = x - hi exactly.  lo is handed over
       // unrounded: the tensor core truncates it to tf32, an error <= 2^-21 |x| whose sign
       // is that of -lo, i.e. unbiased because hi was rounded to nearest.
-      const float* rowp = reinterpret_cast<const float*>(smem + TC_OFF_XPOSE) +
-                          (size_t)slot * 128 * TC_XLD + (size_t)(warp * 32 + lane) * TC_XLD;
+      const float* rowp = atma
+          ? reinterpret_cast<const float*>(smem + TC_OFF_XPOSE + slot * 16384 + my_row * 128)
+          : reinterpret_cast<const float*>(smem + TC_OFF_XPOSE) + (size_t)slot * 128 * TC_XLD + (size_t)my_row * TC_XLD;
+      const int sw = atma ? (my_row & 7) : 0;   // TMA SWIZZLE_128B: 16-byte chunk index ^= row % 8
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float4 x = *reinterpret_cast<const float4*>(rowp + i * 4);
+        float4 x = *reinterpret_cast<const float4*>(rowp + ((i ^ sw) << 2));
+        if (atma && !row_in_box) x = make_float4(0.f, 0.f, 0.f, 0.f);   // rows the box does not cover
         float h;
         h = tf32_rn_fast(x.x); hi[4 * i + 0] = __float_as_uint(h); lo[4 * i + 0] = __float_as_uint(x.x - h);
         h = tf32_rn_fast(x.y); hi[4 * i + 1] = __float_as_uint(h); lo[4 * i + 1] = __float_as_uint(x.y - h);
         h = tf32_rn_fast(x.z); hi[4 * i + 2] = __float_as_uint(h); lo[4 * i + 2] = __float_as_uint(x.z - h);
         h = tf32_rn_fast(x.w); hi[4 * i + 3] = __float_as_uint(h); lo[4 * i + 3] = __float_as_uint(x.w - h);
       }
-      __syncwarp();                         // slot free: refill it right away
+      __syncwarp();                         // slot free
       if (DBG == 6) { long long tq1 = clock64(); tA_x += tq1 - tq0; tq0 = tq1; }
-      if (have) { ensure(tile, sg); issue(sg, k0, slot); advance(); }
-      else cp_async_commit();
+      if (atma) {
+        if (lane == 0) mbar_arrive(bar0 + BR_EMPTY + 8 * slot);
+      } else {
+        if (have) { ensure(tile, sg); issue(sg, k0, slot); advance(); }
+        else cp_async_commit();
+      }
       if (DBG == 6) tA_is += clock64() - tq0;
       long long t0 = 0;
       if (DBG == 6) t0 = clock64();
@@ -439,9 +465,9 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       if (lane == 0) mbar_arrive(bar0 + BA_FULL + 8 * stage);
       if (DBG == 6) tA_st += clock64() - t0;
       if (++stage == TC_ASTAGES) { stage = 0; phase ^= 1; }
-      if (++slot == TC_RSTAGES) slot = 0;
+      if (++slot == TC_RSTAGES) { slot = 0; rphase ^= 1; }
     }
-    cp_async_wait<0>();
+    if (!atma) cp_async_wait<0>();
     if (DBG == 6 && tid == 0 && p.dbg) {
       unsigned long long* d = p.dbg + (size_t)blockIdx.x * 32;
       d[0] = (unsigned long long)tA_n; d[1] = (unsigned long long)tA_wait; d[2] = (unsigned long long)tA_st;
@@ -483,6 +509,32 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         }
       }
       if (DBG == 6 && p.dbg) p.dbg[(size_t)blockIdx.x * 32 + 8] = (unsigned long long)tB_wait;
+    }
+    __syncwarp();
+    } else if (warp == 10) {
+    // ================================================================= A producer by TMA (affine frame maps)
+    if (lane == 0 && p.a_tma) {
+      int slot = 0;
+      uint32_t rphase = 0;
+      const uint32_t bytes = (uint32_t)(p.fpt * J * 128);
+      for (int tile = cid; tile < total_tiles; tile += ncl) {
+        const int f0 = tile_f0(tile);
+        for (int sg = 0; sg < p.nseg; ++sg) {
+          const int Kc = p.seg[sg].Kc;
+          for (int k0 = 0; k0 < p.seg[sg].K; k0 += TC_BK) {
+            const int tap = k0 / Kc;
+            const int mi = p.a_map0[sg] + tap;
+            const CUtensorMap* mp = (mi == 0) ? &amap0 : (mi == 1) ? &amap1 : &amap2;
+            mbar_wait(bar0 + BR_EMPTY + 8 * slot, rphase ^ 1);
+            const uint32_t full = bar0 + BR_FULL + 8 * slot;
+            mbar_arrive_expect_tx(full, bytes);
+            // box {32 channels, J joints, fpt frames} -> fpt*J dense 128-byte rows, swizzled;
+            // frames past the end of the tensor are zero-filled (ragged last tile, dummy tiles)
+            tma_load_3d(sbase + TC_OFF_XPOSE + slot * 16384, mp, full, k0 - tap * Kc, 0, f0);
+            if (++slot == TC_RSTAGES) { slot = 0; rphase ^= 1; }
+          }
+        }
+      }
     }
     __syncwarp();
     } else if (warp == 9) {
@@ -884,8 +936,52 @@ inline bool tc_supported(const GemmP& p, int epi, const TcWeights& t) {
   return true;
 }
 
+// Tensor maps of the A operand: one per (segment, temporal tap), possible when the segment's frame
+// map is affine in the output frame index f:  in_frame = t_mul * f + t_off  (T_in == t_mul * T_out).
+// dims {channels, joints, frames}, box {32, J, fpt}, SWIZZLE_128B, out-of-range frames read as 0.
+struct TcAMaps {
+  CUtensorMap m[3];
+  bool ok = false;
+};
+
+inline void tc_build_amaps(GemmP& p, TcAMaps& am) {
+  am.ok = false;
+  p.a_tma = 0;
+  tc_encode_fn enc = tc_get_encode();
+  if (!enc) return;
+  int nmaps = 0;
+  for (int s = 0; s < p.nseg; ++s) {
+    const ASeg& sg = p.seg[s];
+    const int taps = sg.K / sg.Kc;
+    if ((long long)sg.map.T_in != (long long)sg.map.t_mul * sg.map.T_out) return;   // not affine
+    if (nmaps + taps > 3) return;
+    p.a_map0[s] = nmaps;
+    for (int tp = 0; tp < taps; ++tp) {
+      const float* base = sg.base + (long long)sg.map.t_off * p.J * sg.ld + (long long)tp * sg.tap_stride;
+      cuuint64_t dims[3] = {(cuuint64_t)sg.Kc, (cuuint64_t)p.J, (cuuint64_t)p.F};
+      cuuint64_t strides[2] = {(cuuint64_t)sg.ld * sizeof(float),
+                               (cuuint64_t)sg.map.t_mul * p.J * sg.ld * sizeof(float)};
+      cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)p.J, (cuuint32_t)p.fpt};
+      cuuint32_t estr[3] = {1, 1, 1};
+      if (strides[0] % 16 || strides[1] % 16 || (reinterpret_cast<uintptr_t>(base) & 15)) return;
+      CUresult r = enc(&am.m[nmaps], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides,
+                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return;
+      ++nmaps;
+    }
+  }
+  for (int i = nmaps; i < 3; ++i) am.m[i] = am.m[0];
+  am.ok = nmaps > 0;
+  p.a_tma = am.ok ? 1 : 0;
+}
+
 template <int EPI, int DBG>
-inline int tc_launch_one(int grid, cudaStream_t st, const GemmP& p, const TcWeights& t, int nt, int items) {
+inline int tc_launch_one(int grid, cudaStream_t st, const GemmP& p_in, const TcWeights& t, int nt, int items) {
+  GemmP p = p_in;
+  TcAMaps am;
+  tc_build_amaps(p, am);
+  if (!am.ok) { am.m[0] = t.map_hi; am.m[1] = t.map_hi; am.m[2] = t.map_hi; }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute((const void*)gemm_tc_kernel<EPI, DBG>,
@@ -906,7 +1002,7 @@ inline int tc_launch_one(int grid, cudaStream_t st, const GemmP& p, const TcWeig
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return (int)cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, DBG>, p, t.map_hi, t.map_lo, nt, items);
+  return (int)cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, DBG>, p, t.map_hi, t.map_lo, am.m[0], am.m[1], am.m[2], nt, items);
 }
 
 inline int tc_launch(int sm_count, cudaStream_t st, int epi, const GemmP& p, const TcWeights& t, int dbg = 0) {
