@@ -87,6 +87,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "WAIT_DONE:\n\t"
       "}" ::"r"(bar), "r"(parity) : "memory");
 }
+// non-blocking probe (one try_wait), so that several barriers can be polled with overlapping latency
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -549,6 +560,11 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       uint32_t mcount = 0;                 // main buffers handed out so far
       uint32_t tphase = 0;                 // tile parity (corr buffer)
       long long tM[5] = {0, 0, 0, 0, 0};
+      // The tensor pipe takes one tcgen05.mma at a time from this thread (issuing 12 of them costs
+      // their execution time), so anything else the thread does leaves the pipe idle.  The
+      // readiness probes of the NEXT chunk (~70 cycles each) are therefore launched between the
+      // MMAs of the current one and only consumed at the top of the next iteration.
+      bool pre_a = false, pre_b = false;
       for (int tile = cid; tile < total_tiles; tile += ncl) {
         mbar_wait(bar0 + BC_EMPTY, tphase ^ 1);  // corr buffer drained by the epilogue of the previous tile
         const uint32_t d_corr = tmem_base + CORR_COL;
@@ -559,9 +575,9 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           if (DBG == 6) t0 = clock64();
           if (cg == 0) mbar_wait(bar0 + BM_EMPTY + 8 * mb, ((mcount / NMAIN) & 1) ^ 1);
           if (DBG == 6) t1 = clock64();
-          mbar_wait(bar0 + BA_FULL + 8 * as, aphase);
+          if (!pre_a) mbar_wait(bar0 + BA_FULL + 8 * as, aphase);
           if (DBG == 6) t2 = clock64();
-          mbar_wait(bar0 + BB_FULL + 8 * bs, bphase);
+          if (!pre_b) mbar_wait(bar0 + BB_FULL + 8 * bs, bphase);
           if (DBG == 6) t3 = clock64();
           tc_fence_after();
           const uint32_t d_main = tmem_base + mb * TC_BN;
@@ -569,25 +585,33 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           const uint32_t sb = sbase + bs * TC_STAGE_BYTES;
           const uint64_t b_hi = make_smem_desc(sb), b_lo = make_smem_desc(sb + 16384);
           const bool last_of_group = (cg == TC_FLUSH - 1 || c == nchunks - 1);
-          if (elect_one()) {
+          // ring positions of the next chunk (same rings across tile boundaries)
+          const int as_n = (as + 1 == TC_ASTAGES) ? 0 : as + 1, bs_n = (bs + 1 == TC_BSTAGES) ? 0 : bs + 1;
+          const uint32_t aph_n = (as + 1 == TC_ASTAGES) ? (aphase ^ 1) : aphase;
+          const uint32_t bph_n = (bs + 1 == TC_BSTAGES) ? (bphase ^ 1) : bphase;
 #pragma unroll
-            for (int k = 0; k < TC_BK / 8; ++k) {
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            if (elect_one()) {
               const uint64_t adv = (uint64_t)(k * 2);      // 8 fp32 = 32 B = 2 x 16 B
               umma_tf32_ts(d_main, a_hi + 8 * k, b_hi + adv, TC_IDESC, (cg | k) ? 1u : 0u);
               if (DBG != 3) {
                 umma_tf32_ts(d_corr, a_lo + 8 * k, b_hi + adv, TC_IDESC, (c | k) ? 1u : 0u);
                 umma_tf32_ts(d_corr, a_hi + 8 * k, b_lo + adv, TC_IDESC, 1u);
               }
+              if (k == TC_BK / 8 - 1) {
+                if (TC_CLUSTER > 1) umma_commit_mc(bar0 + BB_EMPTY + 8 * bs, (uint16_t)((1u << TC_CLUSTER) - 1));
+                else umma_commit(bar0 + BB_EMPTY + 8 * bs);     // frees the B smem stage when the MMAs retire
+                umma_commit(bar0 + BA_EMPTY + 8 * as);          // frees the A tmem stage
+                if (last_of_group) umma_commit(bar0 + BM_FULL + 8 * mb);   // group sum ready
+              }
             }
-            if (TC_CLUSTER > 1) umma_commit_mc(bar0 + BB_EMPTY + 8 * bs, (uint16_t)((1u << TC_CLUSTER) - 1));
-            else umma_commit(bar0 + BB_EMPTY + 8 * bs);     // frees the B smem stage when the MMAs retire
-            umma_commit(bar0 + BA_EMPTY + 8 * as);          // frees the A tmem stage
-            if (last_of_group) umma_commit(bar0 + BM_FULL + 8 * mb);   // group sum ready
+            __syncwarp();
+            if (k == 1) pre_a = mbar_try(bar0 + BA_FULL + 8 * as_n, aph_n);
+            if (k == 2) pre_b = mbar_try(bar0 + BB_FULL + 8 * bs_n, bph_n);
           }
-          __syncwarp();
           if (last_of_group) ++mcount;
-          if (++bs == TC_BSTAGES) { bs = 0; bphase ^= 1; }
-          if (++as == TC_ASTAGES) { as = 0; aphase ^= 1; }
+          bs = bs_n; bphase = bph_n;
+          as = as_n; aphase = aph_n;
           if (DBG == 6) {
             const long long t4 = clock64();
             tM[0] += 1; tM[1] += t1 - t0; tM[2] += t2 - t1; tM[3] += t3 - t2; tM[4] += t4 - t3;
@@ -643,12 +667,39 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         }
       }
 
-      // ---- level-2 accumulation: chunk sums (TMEM) -> fp32 registers, round-to-nearest adds
+      // ---- level-2 accumulation: group sums (TMEM) -> fp32 registers, round-to-nearest adds.
+      // The first group is loaded straight into the accumulator registers (4 tcgen05.ld in
+      // flight, one wait); later groups go through 2x32 temporaries.
       float acc[TC_BN];
-#pragma unroll
-      for (int i = 0; i < TC_BN; ++i) acc[i] = 0.f;
       const int ngroups = (nchunks + TC_FLUSH - 1) / TC_FLUSH;
-      for (int c = 0; c < ngroups; ++c) {
+      {
+        const uint32_t mb = mcount % NMAIN;
+        long long t0 = 0;
+        if (DBG == 6) t0 = clock64();
+        mbar_wait(bar0 + BM_FULL + 8 * mb, (mcount / NMAIN) & 1);
+        if (DBG == 6) { tE_n += 1; tE_wait += clock64() - t0; }
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + mb * TC_BN + lane_off;
+        if (DBG == 1 || DBG == 5) {
+#pragma unroll
+          for (int i = 0; i < TC_BN; ++i) acc[i] = 0.f;
+        } else {
+          uint32_t* au = reinterpret_cast<uint32_t*>(acc);
+          tmem_ld32_async(taddr, au);
+          tmem_ld32_async(taddr + 32, au + 32);
+          tmem_ld32_async(taddr + 64, au + 64);
+          tmem_ld32_async(taddr + 96, au + 96);
+          tmem_wait_ld(au);
+          tmem_wait_ld(au + 32);
+          tmem_wait_ld(au + 64);
+          tmem_wait_ld(au + 96);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + BM_EMPTY + 8 * mb);
+        ++mcount;
+      }
+      for (int c = 1; c < ngroups; ++c) {
         const uint32_t mb = mcount % NMAIN;
         long long t0 = 0;
         if (DBG == 6) t0 = clock64();
