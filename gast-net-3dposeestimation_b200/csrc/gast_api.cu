@@ -16,6 +16,8 @@
 #include "gemm_ffma.cuh"
 #include "kernels_misc.cuh"
 #include "gemm_tc.cuh"
+#include "train_kernels.cuh"
+#include "train_state.cuh"
 
 using namespace gast;
 
@@ -75,6 +77,8 @@ struct gast_handle {
   NbrTable nbr[2];
   int nnz[2] = {0, 0};
   std::unordered_map<std::string, Binding> bound;
+  std::unordered_map<std::string, Binding> grads;   // gradient outputs by state_dict key (training)
+  TrainState train;                                  // saved state of the last training forward
   std::vector<void*> owned;          // cudaMalloc'ed derived buffers
   std::vector<BlockConsts> blocks;
   std::vector<StageConsts> stages;
@@ -821,6 +825,78 @@ static int prepare_tc(gast_handle* h, cudaStream_t st) {
     if (prep_one_tc(h, st, s.tc_t, s.Wt, s.Cw, s.taps * s.Cw)) return 1;
     if (prep_one_tc(h, st, s.tc_1, s.W1, s.Cw, s.Cw)) return 1;
   }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// training
+// ------------------------------------------------------------------------------------------
+#include "train.cuh"
+
+extern "C" int gast_bind_grads(gast_t* h, int32_t n, const char* const* keys, void* const* ptrs, const int64_t* numel) {
+  if (!h) return fail("gast_bind_grads: null handle");
+  for (int i = 0; i < n; ++i) h->grads[keys[i]] = Binding{ptrs[i], numel[i]};
+  return 0;
+}
+
+static int train_check(gast_handle* h) {
+  if (h->cfg.kind != GAST_KIND_MODEL) return fail("training is implemented for the MODEL kind only");
+  if (!h->cfg.strided) return fail("training runs the strided (Optimized1f) schedule only, like main.py:166-171; "
+                                   "construct SpatioTemporalModelOptimized1f for training");
+  return 0;
+}
+
+extern "C" size_t gast_train_workspace_bytes(gast_t* h, int32_t B, int32_t T, float dropout_p) {
+  if (!h || train_check(h)) return 0;
+  Arena a{nullptr, 0, 0, true};
+  Lookup L{h};
+  TCtx c{h, nullptr, &a, &L, h->cfg.num_joints, true};
+  TrainState ts;
+  ts.drop_p = dropout_p;
+  if (train_forward(h, c, ts, nullptr, nullptr, B, T)) return 0;
+  if (train_backward(h, c, ts, nullptr)) return 0;
+  return a.off + 512;
+}
+
+extern "C" int gast_forward_train(gast_t* h, const float* x, float* y, int32_t B, int32_t T, float dropout_p,
+                                  uint64_t seed, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return fail("gast_forward_train: null handle");
+  if (train_check(h)) return 1;
+  if (dropout_p < 0.f || dropout_p >= 1.f) return fail("gast_forward_train: dropout_p out of range");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  uintptr_t wsb = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
+  Arena a{reinterpret_cast<char*>(wsb), workspace_bytes, 0, false};
+  Lookup L{h};
+  TCtx c{h, st, &a, &L, h->cfg.num_joints, false};
+  const size_t need = gast_train_workspace_bytes(h, B, T, dropout_p);
+  if (need == 0) return 1;
+  if (!workspace || workspace_bytes < need) return fail("gast_forward_train: workspace too small (%zu < %zu)", workspace_bytes, need);
+  h->launches = 0;
+  h->train = TrainState();
+  h->train.drop_p = dropout_p;
+  h->train.seed = seed;
+  if (train_forward(h, c, h->train, x, y, B, T)) { h->train.valid = false; return 1; }
+  h->train.arena_off = a.off;
+  h->train.valid = true;
+  h->prepared = false;      // running statistics changed: eval constants are stale
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gast_backward(gast_t* h, const float* dy, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return fail("gast_backward: null handle");
+  if (!h->train.valid) return fail("gast_backward: no training forward to differentiate");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  uintptr_t wsb = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
+  Arena a{reinterpret_cast<char*>(wsb), workspace_bytes, h->train.arena_off, false};
+  Lookup L{h};
+  TCtx c{h, st, &a, &L, h->cfg.num_joints, false};
+  if (train_backward(h, c, h->train, dy)) return 1;
+  if (a.off > workspace_bytes) return fail("gast_backward: workspace overrun");
+  h->train.valid = false;
+  CUDA_OK(cudaGetLastError());
   return 0;
 }
 

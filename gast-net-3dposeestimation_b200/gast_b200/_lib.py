@@ -17,7 +17,8 @@ KIND_MODEL, KIND_BLOCK, KIND_LOCAL, KIND_MGLOBAL, KIND_SEMCH, KIND_GLOBAL_HEAD =
 SYMBOLS = ['gast_create', 'gast_destroy', 'gast_bind', 'gast_prepare', 'gast_out_frames',
            'gast_receptive_field', 'gast_workspace_bytes', 'gast_forward',
            'gast_last_launch_count', 'gast_last_tc_launch_count', 'gast_set_timing',
-           'gast_get_timings', 'gast_set_gemm_core', 'gast_debug_gemm', 'gast_last_error', 'gast_version']
+           'gast_get_timings', 'gast_set_gemm_core', 'gast_debug_gemm', 'gast_bind_grads',
+           'gast_train_workspace_bytes', 'gast_forward_train', 'gast_backward', 'gast_last_error', 'gast_version']
 
 
 class GastCfg(C.Structure):
@@ -77,6 +78,14 @@ def load():
     lib.gast_debug_gemm.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.POINTER(C.c_float), vp]
     lib.gast_debug_gemm.restype = C.c_int
+    lib.gast_bind_grads.argtypes = [vp, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(C.c_int64)]
+    lib.gast_bind_grads.restype = C.c_int
+    lib.gast_train_workspace_bytes.argtypes = [vp, C.c_int32, C.c_int32, C.c_float]
+    lib.gast_train_workspace_bytes.restype = C.c_size_t
+    lib.gast_forward_train.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_float, C.c_uint64, vp, C.c_size_t, vp]
+    lib.gast_forward_train.restype = C.c_int
+    lib.gast_backward.argtypes = [vp, vp, vp, C.c_size_t, vp]
+    lib.gast_backward.restype = C.c_int
     lib.gast_last_error.argtypes = []
     lib.gast_last_error.restype = C.c_char_p
     lib.gast_version.argtypes = []

@@ -107,6 +107,24 @@ class _Handle(object):
         _check(self.lib.gast_prepare(self.h, C.c_void_p(stream)), 'gast_prepare')
         self.sig = sig
 
+    def bind_only(self, module):
+        """bind parameter/buffer storage without the eval-mode prepare (training path)"""
+        items = [(k, v) for k, v in module.state_dict(keep_vars=True).items()]
+        n = len(items)
+        keys = (C.c_char_p * n)()
+        ptrs = (C.c_void_p * n)()
+        numel = (C.c_int64 * n)()
+        for i, (k, v) in enumerate(items):
+            if not v.is_cuda or v.device != self.device:
+                raise GastError('parameter %r is on %s, expected %s' % (k, v.device, self.device))
+            if not v.is_contiguous():
+                raise GastError('parameter %r is not contiguous' % k)
+            keys[i] = k.encode()
+            ptrs[i] = v.data_ptr()
+            numel[i] = v.numel()
+        _check(self.lib.gast_bind(self.h, n, keys, ptrs, numel), 'gast_bind')
+        self.sig = None
+
     def forward(self, x, y, B, T, strided_now, stream):
         need = self.lib.gast_workspace_bytes(self.h, B, T, strided_now)
         if need == 0:
@@ -143,6 +161,71 @@ def _stream(device):
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class _TrainFn(torch.autograd.Function):
+    """Training-mode forward/backward of the whole model on the CUDA library (gast_forward_train /
+    gast_backward).  Parameters are passed as inputs so that autograd routes their gradients."""
+
+    @staticmethod
+    def forward(ctx, module, handle, x, names, *params):
+        dev = x.device
+        B, T = int(x.shape[0]), int(x.shape[1])
+        lib = handle.lib
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            handle.bind_only(module)
+            need = lib.gast_train_workspace_bytes(handle.h, B, T, C.c_float(float(module._gast_dropout)))
+            if need == 0:
+                raise GastError('gast_train_workspace_bytes: %s' % L.last_error())
+            ws = torch.empty(int(need), dtype=torch.uint8, device=dev)
+            T_out = lib.gast_out_frames(handle.h, T, 1)
+            if T_out <= 0:
+                raise GastError('forward: %s' % L.last_error())
+            y = torch.empty((B, T_out, module.num_joints_in, 3), dtype=torch.float32, device=dev)
+            p = float(module._gast_dropout)
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
+            _check(lib.gast_forward_train(handle.h, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), B, T,
+                                          C.c_float(p), C.c_uint64(seed), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                          C.c_void_p(st)), 'gast_forward_train')
+        # BatchNorm bookkeeping that torch does in Python: num_batches_tracked (this also bumps the
+        # buffers' versions, so the eval-mode constants are refreshed on the next eval forward)
+        with torch.no_grad():
+            for mod in module.modules():
+                if isinstance(mod, torch.nn.BatchNorm2d):
+                    mod.num_batches_tracked += 1
+        handle.sig = None
+        ctx.handle, ctx.ws, ctx.names, ctx.params = handle, ws, names, params
+        ctx.x = x            # the backward re-reads the input (init_bn statistics): keep it alive
+        ctx.dev = dev
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        handle, ws, names, params = ctx.handle, ctx.ws, ctx.names, ctx.params
+        lib = handle.lib
+        total = sum(p.numel() for p in params)
+        flat = torch.empty(total, dtype=torch.float32, device=ctx.dev)
+        n = len(params)
+        keys = (C.c_char_p * n)()
+        ptrs = (C.c_void_p * n)()
+        numel = (C.c_int64 * n)()
+        views, off = [], 0
+        for i, (k, p) in enumerate(zip(names, params)):
+            v = flat[off:off + p.numel()].view_as(p)
+            views.append(v)
+            keys[i] = k.encode()
+            ptrs[i] = v.data_ptr()
+            numel[i] = p.numel()
+            off += p.numel()
+        dy = dy.contiguous()
+        with torch.cuda.device(ctx.dev):
+            _check(lib.gast_bind_grads(handle.h, n, keys, ptrs, numel), 'gast_bind_grads')
+            _check(lib.gast_backward(handle.h, C.c_void_p(dy.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                     C.c_void_p(_stream(ctx.dev))), 'gast_backward')
+        ctx.ws = None
+        ctx.x = None
+        return (None, None, None, None) + tuple(views)
+
+
 def _no_train(module, what):
     if module.training:
         raise GastError('%s: training-mode forward/backward is not built yet in this round; '
@@ -153,7 +236,6 @@ def _no_train(module, what):
 def run_model(module, x):
     """SpatioTemporalModelBase.forward (gast_net.py:84-104) on the CUDA library."""
     _require_cuda(x, 'SpatioTemporalModel.forward')
-    _no_train(module, 'SpatioTemporalModel.forward')
     dev = x.device
     blk0 = module.layers_graph_conv[0].local_graph_layer
 
@@ -166,6 +248,15 @@ def run_model(module, x):
     h = _handle_for(module, dev, make)
     x = x.contiguous()
     B, T = int(x.shape[0]), int(x.shape[1])
+    if module.training:
+        if not module._gast_strided:
+            raise GastError('training runs on SpatioTemporalModelOptimized1f (strided schedule), which is what '
+                            'the reference trains with (main.py:166-171); the dilated model is eval-only here')
+        names = [k for k, _ in module.named_parameters()]
+        params = [p for _, p in module.named_parameters()]
+        y = _TrainFn.apply(module, h, x, names, *params)
+        module.__dict__['_gast_last_launches'] = h.launches()
+        return y
     # A dilated model fed exactly one receptive field computes only what the strided
     # schedule computes (same arithmetic per output); skip the unused positions.
     strided_now = 1 if (module._gast_strided or

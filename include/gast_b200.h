@@ -117,6 +117,19 @@ int32_t gast_get_timings(gast_t* h, int32_t max_n, float* ms, int32_t* kinds);
  * allows), 1 = force the FP32 FFMA core.  Not a fallback switch: both are CUDA paths. */
 int gast_set_gemm_core(gast_t* h, int32_t core);
 
+/* ---- training (SpatioTemporalModelOptimized1f in train() mode, main.py:213-243) -------------------
+ * gast_forward_train: forward with batch-statistics BatchNorm (running stats of the bound buffers
+ *   are updated in place, momentum 0.1) and Dropout(p) driven by `seed`; keeps what the backward
+ *   needs in `workspace` (must stay untouched until gast_backward).  x (B,T,J,F) -> y (B,T_out,J,3).
+ * gast_backward: dy (B,T_out,J,3) -> gradient of every parameter, WRITTEN (not accumulated) into the
+ *   buffers bound with gast_bind_grads (same keys as gast_bind; buffers/running stats have none).
+ * Only the strided schedule trains, like the reference (main.py:166-171). */
+int gast_bind_grads(gast_t* h, int32_t n, const char* const* keys, void* const* dev_ptrs, const int64_t* numel);
+size_t gast_train_workspace_bytes(gast_t* h, int32_t B, int32_t T, float dropout_p);
+int gast_forward_train(gast_t* h, const float* x, float* y, int32_t B, int32_t T, float dropout_p, uint64_t seed,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int gast_backward(gast_t* h, const float* dy, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Test/probe entry (not on the forward path): out[M,N] = A[M,K] . W[N,K]^T on one GEMM core
  * (core 0 = tcgen05 3xTF32, 1 = FFMA).  tc_mode != 0 selects a timing-experiment variant of the
  * tcgen05 kernel (parts disabled; results invalid).  Runs once, then `reps` timed launches
