@@ -635,7 +635,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     const int fb = fr * J;                   // first row of this thread's frame
     uint32_t mcount = 0;
     uint32_t tphase = 0;
-    long long tE_n = 0, tE_wait = 0, tE_tot = clock64();
+    long long tE_n = 0, tE_wait = 0, tE_tot = clock64(), tE_tiles = 0, tE_cw = 0, tE_cl = 0, tE_ep = 0, tE_fl = 0;
     const uint32_t lane_off = (uint32_t)(ew * 32) << 16;
     for (int tile = cid; tile < total_tiles; tile += ncl) {
       const int tn = tile % n_tiles_n;
@@ -677,7 +677,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         long long t0 = 0;
         if (DBG == 6) t0 = clock64();
         mbar_wait(bar0 + BM_FULL + 8 * mb, (mcount / NMAIN) & 1);
-        if (DBG == 6) { tE_n += 1; tE_wait += clock64() - t0; }
+        if (DBG == 6) { tE_n += 1; tE_wait += clock64() - t0; t0 = clock64(); }
         tc_fence_after();
         const uint32_t taddr = tmem_base + mb * TC_BN + lane_off;
         if (DBG == 1 || DBG == 5) {
@@ -698,6 +698,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         __syncwarp();
         if (lane == 0) mbar_arrive(bar0 + BM_EMPTY + 8 * mb);
         ++mcount;
+        if (DBG == 6) tE_fl += clock64() - t0;
       }
       for (int c = 1; c < ngroups; ++c) {
         const uint32_t mb = mcount % NMAIN;
@@ -725,8 +726,11 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         if (lane == 0) mbar_arrive(bar0 + BM_EMPTY + 8 * mb);
         ++mcount;
       }
+      long long tc0 = 0;
+      if (DBG == 6) tc0 = clock64();
       {
         mbar_wait(bar0 + BC_FULL, tphase);
+        if (DBG == 6) { long long t1 = clock64(); tE_cw += t1 - tc0; tc0 = t1; }
         tc_fence_after();
         const uint32_t taddr = tmem_base + CORR_COL + lane_off;
 #pragma unroll
@@ -746,6 +750,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         __syncwarp();
         if (lane == 0) mbar_arrive(bar0 + BC_EMPTY);
         tphase ^= 1;
+        if (DBG == 6) { long long t1 = clock64(); tE_cl += t1 - tc0; tc0 = t1; ++tE_tiles; }
       }
 
       if (EPI == EPI_PLAIN) {
@@ -878,6 +883,10 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       }
     }
     if (DBG == 6 && et == 0 && p.dbg) {
+      p.dbg[(size_t)blockIdx.x * 32 + 27] = (unsigned long long)tE_tiles;
+      p.dbg[(size_t)blockIdx.x * 32 + 28] = (unsigned long long)tE_cw;
+      p.dbg[(size_t)blockIdx.x * 32 + 29] = (unsigned long long)tE_cl;
+      p.dbg[(size_t)blockIdx.x * 32 + 30] = (unsigned long long)tE_fl;
       p.dbg[(size_t)blockIdx.x * 32 + 24] = (unsigned long long)tE_n;
       p.dbg[(size_t)blockIdx.x * 32 + 25] = (unsigned long long)tE_wait;
       p.dbg[(size_t)blockIdx.x * 32 + 26] = (unsigned long long)(clock64() - tE_tot);

@@ -63,6 +63,8 @@ def perf():
                   % (d[:, 4].mean() / nA, d[:, 5].mean() / nA, d[:, 6].mean() / nA, d[:, 1].mean() / nA, d[:, 2].mean() / nA, d[:, 3].mean() / nA, d[:, 8].mean() / nM,
                      d[:, 17].mean() / nM, d[:, 18].mean() / nM, d[:, 19].mean() / nM, d[:, 20].mean() / nM,
                      d[:, 25].mean() / nE, d[:, 26].mean() / nE), flush=True)
+            nT = max(d[:, 27].mean(), 1)
+            print('   epilogue per tile [cycles]: total %.0f | first-group flush %.0f | wait corr %.0f | corr load+add %.0f | => bias/act/store ~%.0f' % (d[:, 26].mean() / nT, d[:, 30].mean() / nT, d[:, 28].mean() / nT, d[:, 29].mean() / nT, (d[:, 26].mean() - d[:, 25].mean() - d[:, 30].mean() - d[:, 28].mean() - d[:, 29].mean()) / nT), flush=True)
         else:
             print('   dbg6 failed:', _lib.last_error())
 
