@@ -754,22 +754,42 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       }
 
       if (EPI == EPI_PLAIN) {
-        if (valid) {
-          const float* resrow = nullptr;
-          if (p.res) {
-            long long fin = map_frame(p.res_map, f0 + fr);
-            resrow = p.res + (fin * J + ji) * (long long)p.res_ld;
-          }
+        // Row-per-thread registers -> warp-private smem patch -> COALESCED 128-bit stores (8 lanes
+        // cover one 128-byte row segment).  Storing straight from the row-per-thread layout issues
+        // 32 half-sector writes per instruction: clock64 attribution showed ~7500 of the ~8000
+        // epilogue cycles of a tile in those stores (profiles/r01_tc_attribution.md).
+        float* patch = staging + ew * (32 * TC_XLD);
+        const int rsub = lane >> 3, ch = lane & 7;
 #pragma unroll
-          for (int g = 0; g < 32; ++g) {
-            const int n = n0 + g * 4;
-            if (n < p.N) {
-              float4 o = make_float4(acc[g * 4], acc[g * 4 + 1], acc[g * 4 + 2], acc[g * 4 + 3]);
-              if (p.bias) { float4 bb = ldg4(p.bias + n); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
+        for (int q = 0; q < 4; ++q) {
+          const int nq = n0 + q * 32;
+          if (nq < p.N) {                       // warp-uniform
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const int n = nq + g * 4;
+              float4 o = make_float4(acc[q * 32 + g * 4], acc[q * 32 + g * 4 + 1], acc[q * 32 + g * 4 + 2],
+                                     acc[q * 32 + g * 4 + 3]);
+              if (p.bias && n < p.N) { float4 bb = ldg4(p.bias + n); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
               if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-              if (resrow) { float4 rr = ldg4(resrow + n); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
-              *reinterpret_cast<float4*>(p.out + orow * p.ld_out + n) = o;
+              *reinterpret_cast<float4*>(patch + lane * TC_XLD + g * 4) = o;
             }
+            __syncwarp();
+            const int n = nq + ch * 4;
+#pragma unroll 2
+            for (int i = 0; i < 8; ++i) {
+              const int rr = ew * 32 + 4 * i + rsub;          // tile row stored by this lane
+              if (rr < vrows && n < p.N) {
+                float4 o = *reinterpret_cast<const float4*>(patch + (4 * i + rsub) * TC_XLD + ch * 4);
+                if (p.res) {
+                  const int frr = rr / J, jr = rr - frr * J;
+                  const float4 r4 = ldg4(p.res + (map_frame(p.res_map, f0 + frr) * J + jr) * (long long)p.res_ld + n);
+                  o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                }
+                // rows of a tile are consecutive in the output: row index = f0*J + rr
+                *reinterpret_cast<float4*>(p.out + ((long long)f0 * J + rr) * p.ld_out + n) = o;
+              }
+            }
+            __syncwarp();
           }
         }
       } else if (EPI == EPI_SEMCH) {
