@@ -51,15 +51,18 @@ constexpr int TC_CLUSTER = GAST_TC_CLUSTER;   // CTAs per cluster: same N tile, 
 constexpr int TC_THREADS = 384;   // 3 warpgroups: A producers | accumulate+epilogue | TMA, MMA, 2 idle
 constexpr int TC_STAGE_BYTES = 2 * 16384;            // B_hi, B_lo : 128 rows x 128 B each
 constexpr int TC_SLD = 68;                            // staging row stride (floats): conflict-free 16B rows
-constexpr int TC_MAX_NNZ = 64;
+constexpr int TC_MAX_NNZ = 64;    // SemCH coefficient slab rows
+constexpr int TC_COEF_ROWS = 68;   // slab size in rows of TC_SLD floats (also holds the 4 output patches of the global epilogue)
 constexpr int TC_JMAX = 20;
 constexpr int TC_OFF_STAGING = TC_BSTAGES * TC_STAGE_BYTES;
 constexpr int TC_OFF_COEF = TC_OFF_STAGING + 128 * TC_SLD * 4;
-constexpr int TC_OFF_AB = TC_OFF_COEF + TC_MAX_NNZ * TC_SLD * 4;
+constexpr int TC_OFF_AB = TC_OFF_COEF + TC_COEF_ROWS * TC_SLD * 4;
 constexpr int TC_XLD = 36;                            // raw A row stride (floats): conflict-free row-per-thread reads
-constexpr int TC_OFF_XPOSE = TC_OFF_AB + 128 * 8 * 4;  // raw A ring: TC_RSTAGES x 128 rows x 36 floats
+constexpr int TC_OFF_XPOSE = (TC_OFF_AB + 128 * 8 * 4 + 1023) / 1024 * 1024;  // raw A ring (1024-aligned: TMA SWIZZLE_128B)
 constexpr int TC_OFF_BAR = TC_OFF_XPOSE + TC_RSTAGES * 128 * TC_XLD * 4;
-constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 256 + 1024;   // 12 mbarriers + tmem ptr   // + alignment slack
+static_assert(TC_OFF_STAGING % 1024 == 0 && TC_OFF_XPOSE % 1024 == 0, "swizzled regions must be 1024-byte aligned");
+constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 256 + 1024;
+static_assert(TC_SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");   // 12 mbarriers + tmem ptr   // + alignment slack
 
 // ----------------------------------------------------------------------------------------
 // PTX wrappers
@@ -803,8 +806,9 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
               make_float4(acc[64 + g * 4], acc[64 + g * 4 + 1], acc[64 + g * 4 + 2], acc[64 + g * 4 + 3]);
         const float* h0 = acc;
         epi_bar_sync();
-        if (valid) {
-          const int z0 = nb.row_ptr[ji], z1 = nb.row_ptr[ji + 1];
+        float ov[64];
+        {
+          const int z0 = valid ? nb.row_ptr[ji] : 0, z1 = valid ? nb.row_ptr[ji + 1] : 0;
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq) {           // 16 channels at a time
             float o[16];
@@ -830,14 +834,25 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
               }
             }
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int c = c0 + gq * 16 + g * 4;
-              if (c < p.C) {
-                float4 ov = make_float4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
-                if (p.relu) { ov.x = fmaxf(ov.x, 0.f); ov.y = fmaxf(ov.y, 0.f); ov.z = fmaxf(ov.z, 0.f); ov.w = fmaxf(ov.w, 0.f); }
-                *reinterpret_cast<float4*>(p.out + orow * p.ld_out + mask * p.C + c) = ov;
-              }
-            }
+            for (int g = 0; g < 16; ++g) ov[gq * 16 + g] = p.relu ? fmaxf(o[g], 0.f) : o[g];
+          }
+        }
+        epi_bar_sync();      // every neighbour read of the staged H1 tile is done: reuse it for the output
+#pragma unroll
+        for (int g = 0; g < 16; ++g)
+          *reinterpret_cast<float4*>(staging + r * TC_SLD + g * 4) =
+              make_float4(ov[g * 4], ov[g * 4 + 1], ov[g * 4 + 2], ov[g * 4 + 3]);
+        __syncwarp();
+        {
+          // coalesced: 16 lanes cover the 256-byte row segment of one row, 2 rows per instruction
+          const int rs = lane >> 4, chq = lane & 15;
+          const int c = c0 + chq * 4;
+#pragma unroll 4
+          for (int i = 0; i < 16; ++i) {
+            const int rr = ew * 32 + 2 * i + rs;
+            if (rr < vrows && c < p.C)
+              *reinterpret_cast<float4*>(p.out + ((long long)f0 * J + rr) * p.ld_out + mask * p.C + c) =
+                  *reinterpret_cast<const float4*>(staging + rr * TC_SLD + chq * 4);
           }
         }
         epi_bar_sync();      // staging / coef slab free for the next tile
@@ -856,6 +871,8 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
                             acc[half * 64 + g * 4 + 2] + bb.z, acc[half * 64 + g * 4 + 3] + bb.w);
           }
           epi_bar_sync();
+          // (a register/patch-staged, coalesced-store variant of this mix measured 70 % slower than the
+          //  direct row-per-thread stores below: profiles/r01_tc_attribution.md)
           if (valid && nb0 < p.N) {
             const int nend = min(nb0 + 64, p.N);
             const int h_lo = nb0 / p.Cg, h_hi = (nend - 1) / p.Cg;
