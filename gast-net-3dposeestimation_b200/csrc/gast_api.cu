@@ -746,7 +746,9 @@ extern "C" int gast_forward(gast_t* h, const float* x, float* y, int32_t B, int3
   long long F = (long long)B * g.T0;
   {
     long long rows = F * J;
-    long long thr = rows * (C / 4);
+    if (rows >= 0x7fffffffLL) return fail("expand: more than 2^31 positions in one call");
+    if (c.filter_widths[0] * c.in_features > EXP_MAXKF) return fail("expand: filter_width*in_features > %d unsupported", EXP_MAXKF);
+    long long thr = ((rows + EXP_ROWS - 1) / EXP_ROWS) * (C / 4);
     TimedLaunch tl(h, st, LK_EXPAND);
     expand_kernel<<<cdiv(thr, 256), 256, 0, st>>>(x, h->We, h->be, mb.act[0], rows, J, T, g.T0, g.s0,
                                                  c.filter_widths[0], c.in_features, C);
