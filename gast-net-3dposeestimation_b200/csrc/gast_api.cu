@@ -595,7 +595,10 @@ static int launch_rowdot(gast_handle* h, cudaStream_t st, const float* X, int ld
   const int Q = 2 * b.heads;
   unsigned blocks = cdiv(rows * 32, 256);
   TimedLaunch tl(h, st, LK_ROWDOT);
-  if (Q == 8) rowdot_kernel<8><<<blocks, 256, 0, st>>>(X, ldx, b.U, b.cab, ab, rows, b.C);
+  if (Q == 8 && b.C % 4 == 0 && (size_t)8 * b.C * sizeof(float) <= 48 * 1024) {
+    unsigned g = (unsigned)std::min<long long>((rows * 32 + 255) / 256, (long long)h->sm_count * 8);
+    rowdot8_kernel<<<g, 256, sizeof(float) * 8 * b.C, st>>>(X, ldx, b.U, b.cab, ab, rows, b.C);
+  } else if (Q == 8) rowdot_kernel<8><<<blocks, 256, 0, st>>>(X, ldx, b.U, b.cab, ab, rows, b.C);
   else if (Q == 6) rowdot_kernel<6><<<blocks, 256, 0, st>>>(X, ldx, b.U, b.cab, ab, rows, b.C);
   else if (Q == 4) rowdot_kernel<4><<<blocks, 256, 0, st>>>(X, ldx, b.U, b.cab, ab, rows, b.C);
   else if (Q == 2) rowdot_kernel<2><<<blocks, 256, 0, st>>>(X, ldx, b.U, b.cab, ab, rows, b.C);
@@ -827,6 +830,44 @@ static int prepare_tc(gast_handle* h, cudaStream_t st) {
     if (prep_one_tc(h, st, s.tc_t, s.Wt, s.Cw, s.taps * s.Cw)) return 1;
     if (prep_one_tc(h, st, s.tc_1, s.W1, s.Cw, s.Cw)) return 1;
   }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// test-time augmentation around the forward
+// ------------------------------------------------------------------------------------------
+static int make_perm(int J, int n, const int32_t* left, const int32_t* right, JointPerm* p) {
+  if (J < 1 || J > 32) return fail("tta: J out of range");
+  for (int j = 0; j < 32; ++j) p->p[j] = (unsigned char)j;
+  for (int k = 0; k < n; ++k) {
+    if (left[k] < 0 || left[k] >= J || right[k] < 0 || right[k] >= J) return fail("tta: joint index out of range");
+    p->p[left[k]] = (unsigned char)right[k];
+    p->p[right[k]] = (unsigned char)left[k];
+  }
+  return 0;
+}
+
+extern "C" int gast_tta_prepare(const float* seq, float* out, int32_t T, int32_t J, int32_t F, int32_t pad,
+                                int32_t causal_shift, int32_t n_sym, const int32_t* kps_left, const int32_t* kps_right,
+                                void* stream) {
+  if (T <= 0 || F <= 0 || pad < 0 || causal_shift < 0 || causal_shift > pad) return fail("gast_tta_prepare: bad arguments");
+  JointPerm perm;
+  if (make_perm(J, n_sym, kps_left, kps_right, &perm)) return 1;
+  const long long n = (long long)(T + 2 * pad) * J * F;
+  tta_prepare_kernel<<<cdiv(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      seq, out, T, J, F, pad + causal_shift, pad - causal_shift, perm);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gast_tta_merge(const float* pred, float* out, int32_t T, int32_t J, int32_t n_sym,
+                              const int32_t* joints_left, const int32_t* joints_right, void* stream) {
+  if (T <= 0) return fail("gast_tta_merge: bad arguments");
+  JointPerm perm;
+  if (make_perm(J, n_sym, joints_left, joints_right, &perm)) return 1;
+  const long long n = (long long)T * J * 3;
+  tta_merge_kernel<<<cdiv(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pred, out, T, J, perm);
+  CUDA_OK(cudaGetLastError());
   return 0;
 }
 

@@ -90,6 +90,55 @@ __global__ void rowdot_kernel(const float* __restrict__ X, int ldx, const float*
   }
 }
 
+// Q = 8 (4 heads) version: U staged in shared memory, a warp walks rows with a grid stride, and the
+// 8 partial sums are reduced with a halving butterfly (9 shuffles instead of 40).
+__global__ void rowdot8_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ U,
+                               const float* __restrict__ cab, float* __restrict__ ab, long long rows, int K) {
+  extern __shared__ __align__(16) float us[];          // [8][K]
+  for (int i = threadIdx.x * 4; i < 8 * K; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(us + i) = ldg4(U + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int sel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);   // q owned after the butterfly
+  const float cq = __ldg(cab + sel);
+  for (long long row = warp; row < rows; row += nwarps) {
+    const float* xr = X + row * ldx;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 xv = ldg4(xr + k);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 u = *reinterpret_cast<const float4*>(us + q * K + k);
+        v[q] = fmaf(xv.x, u.x, fmaf(xv.y, u.y, fmaf(xv.z, u.z, fmaf(xv.w, u.w, v[q]))));
+      }
+    }
+    // halving butterfly: after the xor-16 step a lane keeps 4 of the 8 sums, then 2, then 1
+    float w4[4], w2[2], w1;
+    const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float keep = hi16 ? v[i + 4] : v[i], send = hi16 ? v[i] : v[i + 4];
+      w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float keep = hi8 ? w4[i + 2] : w4[i], send = hi8 ? w4[i] : w4[i + 2];
+      w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    {
+      const float keep = hi4 ? w2[1] : w2[0], send = hi4 ? w2[0] : w2[1];
+      w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+    w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+    if ((lane & 3) == 0) ab[row * 8 + sel] = w1 + cq;
+  }
+}
+
 // shrink (gast_net.py:60,99): y[row][o] = X[row,:] . Ws[o,:], o < 3.   Warp per row.
 __global__ void shrink_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ Ws,
                               float* __restrict__ y, long long rows, int K) {
@@ -107,6 +156,43 @@ __global__ void shrink_kernel(const float* __restrict__ X, int ldx, const float*
   }
   a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
   if (lane == 0) { y[row * 3 + 0] = a0; y[row * 3 + 1] = a1; y[row * 3 + 2] = a2; }
+}
+
+// ---------------------------------------------------------------------------------------
+// Test-time augmentation on the device: the caller-side steps either side of
+// the forward in reconstruction.evaluate / main.evaluate.
+// ---------------------------------------------------------------------------------------
+struct JointPerm { unsigned char p[32]; };   // left<->right partner of every joint (identity elsewhere)
+
+// UnchunkedGenerator.next_epoch with augment=True (common/generators.py:210-233):
+// out[0] = edge-padded sequence, out[1] = its mirrored twin (x *= -1, left/right keypoints swapped)
+__global__ void tta_prepare_kernel(const float* __restrict__ seq, float* __restrict__ out, int T, int J, int F,
+                                   int pad_l, int pad_r, JointPerm perm) {
+  const int Tp = T + pad_l + pad_r;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long n = (long long)Tp * J * F;
+  if (idx >= n) return;
+  int c = (int)(idx % F);
+  int j = (int)((idx / F) % J);
+  int t = (int)(idx / ((long long)F * J));
+  int ts = min(max(t - pad_l, 0), T - 1);
+  out[idx] = seq[((long long)ts * J + j) * F + c];
+  float v = seq[((long long)ts * J + perm.p[j]) * F + c];
+  out[n + idx] = (c == 0) ? -v : v;
+}
+
+// un-flip + average (main.py:314-318, reconstruction.py:163-167): out = mean(pred[0], unflip(pred[1]))
+__global__ void tta_merge_kernel(const float* __restrict__ pred, float* __restrict__ out, int T, int J,
+                                 JointPerm perm) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long n = (long long)T * J * 3;
+  if (idx >= n) return;
+  int c = (int)(idx % 3);
+  int j = (int)((idx / 3) % J);
+  long long t = idx / (3LL * J);
+  float b = pred[n + (t * J + perm.p[j]) * 3 + c];
+  if (c == 0) b = -b;
+  out[idx] = (pred[idx] + b) / 2.0f;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -18,7 +18,7 @@ SYMBOLS = ['gast_create', 'gast_destroy', 'gast_bind', 'gast_prepare', 'gast_out
            'gast_receptive_field', 'gast_workspace_bytes', 'gast_forward',
            'gast_last_launch_count', 'gast_last_tc_launch_count', 'gast_set_timing',
            'gast_get_timings', 'gast_set_gemm_core', 'gast_debug_gemm', 'gast_bind_grads',
-           'gast_train_workspace_bytes', 'gast_forward_train', 'gast_backward', 'gast_last_error', 'gast_version']
+           'gast_train_workspace_bytes', 'gast_forward_train', 'gast_backward', 'gast_tta_prepare', 'gast_tta_merge', 'gast_last_error', 'gast_version']
 
 
 class GastCfg(C.Structure):
@@ -86,6 +86,11 @@ def load():
     lib.gast_forward_train.restype = C.c_int
     lib.gast_backward.argtypes = [vp, vp, vp, C.c_size_t, vp]
     lib.gast_backward.restype = C.c_int
+    ip = C.POINTER(C.c_int32)
+    lib.gast_tta_prepare.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, ip, ip, vp]
+    lib.gast_tta_prepare.restype = C.c_int
+    lib.gast_tta_merge.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, ip, ip, vp]
+    lib.gast_tta_merge.restype = C.c_int
     lib.gast_last_error.argtypes = []
     lib.gast_last_error.restype = C.c_char_p
     lib.gast_version.argtypes = []

@@ -117,6 +117,18 @@ int32_t gast_get_timings(gast_t* h, int32_t max_n, float* ms, int32_t* kinds);
  * allows), 1 = force the FP32 FFMA core.  Not a fallback switch: both are CUDA paths. */
 int gast_set_gemm_core(gast_t* h, int32_t core);
 
+/* ---- test-time augmentation around the forward (the caller-side steps of reconstruction.evaluate /
+ * main.evaluate, kept on the device) -----------------------------------------------------------------
+ * gast_tta_prepare: UnchunkedGenerator.next_epoch(augment=True) (common/generators.py:210-233):
+ *   seq (T,J,F) -> out (2, T+2*pad, J, F): edge padding (pad+causal_shift left, pad-causal_shift right)
+ *   and the mirrored twin (feature 0 negated, kps_left[k] <-> kps_right[k] swapped).
+ * gast_tta_merge: main.py:314-318: pred (2,T,J,3) -> out (T,J,3) = mean(pred[0], un-flipped pred[1]).
+ * Index lists are host arrays of n_sym entries. */
+int gast_tta_prepare(const float* seq, float* out, int32_t T, int32_t J, int32_t F, int32_t pad, int32_t causal_shift,
+                     int32_t n_sym, const int32_t* kps_left, const int32_t* kps_right, void* stream);
+int gast_tta_merge(const float* pred, float* out, int32_t T, int32_t J, int32_t n_sym, const int32_t* joints_left,
+                   const int32_t* joints_right, void* stream);
+
 /* ---- training (SpatioTemporalModelOptimized1f in train() mode, main.py:213-243) -------------------
  * gast_forward_train: forward with batch-statistics BatchNorm (running stats of the bound buffers
  *   are updated in place, momentum 0.1) and Dropout(p) driven by `seed`; keeps what the backward

@@ -293,3 +293,23 @@ def mpjpe(pred, target):
     """common/loss.py:5-11."""
     assert pred.shape == target.shape
     return float(np.mean(np.linalg.norm(pred.astype(np.float64) - target.astype(np.float64), axis=-1)))
+
+
+# --------------------------------------------------------------------------------------
+# test-time augmentation around the forward (SURVEY.md §8f N1)
+# --------------------------------------------------------------------------------------
+def tta_prepare(seq, pad, causal_shift, kps_left, kps_right):
+    """UnchunkedGenerator.next_epoch with augment=True, common/generators.py:210-233."""
+    b = np.expand_dims(np.pad(seq, ((pad + causal_shift, pad - causal_shift), (0, 0), (0, 0)), 'edge'), axis=0)
+    b = np.concatenate((b, b), axis=0)
+    b[1, :, :, 0] *= -1
+    b[1, :, kps_left + kps_right] = b[1, :, kps_right + kps_left]
+    return b.astype(np.float32)
+
+
+def tta_merge(pred, joints_left, joints_right):
+    """main.py:314-318 / reconstruction.py:163-167."""
+    p = pred.copy()
+    p[1, :, :, 0] *= -1
+    p[1, :, joints_left + joints_right] = p[1, :, joints_right + joints_left]
+    return np.mean(p, axis=0, keepdims=True).squeeze(0)

@@ -20,7 +20,8 @@ def pytest_configure(config):
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN, name + '.npz'))
     d = {k: z[k] for k in z.files if k != 'meta'}
-    d['meta'] = json.loads(str(z['meta']))
+    if 'meta' in z.files:
+        d['meta'] = json.loads(str(z['meta']))
     return d
 
 

@@ -93,6 +93,28 @@ def baseball_input():
     return b2.astype(np.float32)
 
 
+def tta_cases():
+    """N1 goldens: the reference's own UnchunkedGenerator (common/generators.py:162-236) builds the
+    padded + mirrored batch; the un-flip/average is main.py:314-318 executed with torch."""
+    from common.generators import UnchunkedGenerator
+    left, right = [4, 5, 6, 11, 12, 13], [1, 2, 3, 14, 15, 16]
+    rs = np.random.RandomState(11)
+    seq = rs.standard_normal((37, 17, 2)).astype(np.float32)
+    out = {'seq': seq}
+    for name, pad, shift in (('sym', 13, 0), ('causal', 13, 13), ('pad40', 40, 0)):
+        gen = UnchunkedGenerator(None, None, [seq], pad=pad, causal_shift=shift, augment=True,
+                                 kps_left=left, kps_right=right, joints_left=left, joints_right=right)
+        (_, _, batch_2d), = list(gen.next_epoch())
+        out['batch_' + name] = batch_2d.astype(np.float32)
+    pred = torch.from_numpy(rs.standard_normal((2, 37, 17, 3)).astype(np.float32))
+    out['pred'] = pred.numpy().copy()
+    pred[1, :, :, 0] *= -1                                                    # main.py:315
+    pred[1, :, left + right] = pred[1, :, right + left]                       # main.py:316
+    out['merged'] = torch.mean(pred, dim=0, keepdim=True).numpy()             # main.py:317
+    np.savez_compressed(os.path.join(HERE, 'tta_17.npz'), **out)
+    print('tta_17', {k: v.shape for k, v in out.items()})
+
+
 def module_cases():
     J, C = 17, 32
     adj = adj_for(J)
@@ -167,4 +189,8 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'tta':
+        tta_cases()
+    else:
+        main()
+        tta_cases()

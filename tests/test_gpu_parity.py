@@ -227,3 +227,28 @@ def test_baseline_configs_vs_torch_port(J, fw, ch, B, T, core):
     # to that scale: |delta| <= 1e-3 mm per 1000 mm of MPJPE (and never looser than 2e-3 mm)
     a, b = mp(y[:n_ref]), mp(ref)
     assert abs(a - b) <= max(1e-3, 1e-3 * b / 1000.0), (a, b)
+
+
+def test_tta_on_device_matches_reference_generator():
+    """N1: edge padding + mirrored twin and un-flip/average on the device, bit-exact against what the
+    reference's UnchunkedGenerator / main.py:314-318 produced (golden tta_17), then the whole
+    evaluate_sequence on the real baseball clip of reconstruction.py."""
+    from oracle import gast_oracle as O
+    from gast_b200 import tta
+    left, right = [4, 5, 6, 11, 12, 13], [1, 2, 3, 14, 15, 16]
+    t = load_golden('tta_17')
+    seq = torch.from_numpy(t['seq']).cuda()
+    for name, pad, shift in (('sym', 13, 0), ('causal', 13, 13), ('pad40', 40, 0)):
+        got = tta.tta_prepare(seq, pad, shift, left, right).cpu().numpy()
+        assert np.array_equal(got, t['batch_' + name]), name
+    merged = tta.tta_merge(torch.from_numpy(t['pred']).cuda(), left, right).cpu().numpy()
+    assert np.array_equal(merged, t['merged'][0])
+    with pytest.raises(RuntimeError):
+        tta.tta_prepare(seq, 13, 0, [40], [1])
+    g = load_golden('cfg1_baseball_17_333_c128')
+    clip = g['x'][0, 13:-13]                                  # the un-padded keypoints
+    assert np.array_equal(tta.tta_prepare(torch.from_numpy(clip).cuda(), 13, 0, left, right).cpu().numpy(), g['x'])
+    m = build_model(g['meta'])
+    out = tta.evaluate_sequence(m, clip, left, right, left, right)
+    assert out.shape == (277, 17, 3)
+    assert np.abs(out.cpu().numpy() - O.tta_merge(g['y'], left, right)).max() < TOL

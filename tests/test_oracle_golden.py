@@ -132,3 +132,15 @@ def test_torch_ref_train_mode_matches_numpy_oracle_batch_stats():
     with torch.no_grad():
         yt = TR.forward(torch.from_numpy(g['x']), p, masks, m['filter_widths'], strided=True, training=True).numpy()
     assert np.abs(yn - yt).max() < 5e-5
+
+
+def test_tta_restatement_matches_reference_generator():
+    """oracle.tta_prepare / tta_merge against batches the reference's UnchunkedGenerator built and the
+    un-flip/average of main.py:314-318 (tests/golden/make_golden.py:tta_cases)."""
+    g = load_golden('tta_17')
+    left, right = [4, 5, 6, 11, 12, 13], [1, 2, 3, 14, 15, 16]
+    for name, pad, shift in (('sym', 13, 0), ('causal', 13, 13), ('pad40', 40, 0)):
+        assert np.array_equal(O.tta_prepare(g['seq'], pad, shift, left, right), g['batch_' + name])
+    assert np.array_equal(O.tta_merge(g['pred'], left, right), g['merged'][0])
+    b = load_golden('cfg1_baseball_17_333_c128')['x']
+    assert np.array_equal(O.tta_prepare(b[0, 13:-13], 13, 0, left, right), b)
