@@ -807,9 +807,9 @@ extern "C" int gast_forward(gast_t* h, const float* x, float* y, int32_t B, int3
 // ------------------------------------------------------------------------------------------
 // tcgen05 weight copies
 // ------------------------------------------------------------------------------------------
-static int prep_one_tc(gast_handle* h, cudaStream_t st, TcWeights& t, const float* W, int N, int K) {
+static int prep_one_tc(gast_handle* h, cudaStream_t st, TcWeights& t, const float* W, int N, int K, int semch = 0) {
   if (!W) return 0;
-  int rc = tc_prepare_weights(t, W, N, K, st, &h->owned);
+  int rc = tc_prepare_weights(t, W, N, K, st, &h->owned, semch);
   if (rc) return fail("tcgen05 weight preparation failed (%d): %s", rc,
                       rc > 0 ? cudaGetErrorString((cudaError_t)rc) : "cuTensorMapEncodeTiled unavailable/failed");
   return 0;
@@ -820,7 +820,7 @@ static int prepare_tc(gast_handle* h, cudaStream_t st) {
   for (BlockConsts& b : h->blocks) {
     const int C = b.C;
     const int nmask = (kind == GAST_KIND_SEMCH) ? 1 : 2;
-    if (prep_one_tc(h, st, b.tc_loc, b.Wloc, nmask * b.tpm * 128, C)) return 1;
+    if (prep_one_tc(h, st, b.tc_loc, b.Wloc, nmask * b.tpm * 128, C, 1)) return 1;
     if (prep_one_tc(h, st, b.tc_lc, b.Wlc, C, 2 * C)) return 1;
     if (prep_one_tc(h, st, b.tc_g, b.Wg, b.heads * b.Cg, C)) return 1;
     if (prep_one_tc(h, st, b.tc_gc, b.Wgc, C, C)) return 1;
@@ -1013,3 +1013,8 @@ extern "C" int gast_debug_gemm(const float* A, const float* W, float* out, int32
   if (rc || e != cudaSuccess) return fail("gast_debug_gemm: %s", cudaGetErrorString(rc ? (cudaError_t)rc : e));
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// callers / data formats either side of the forward
+// ------------------------------------------------------------------------------------------
+#include "pipeline.cuh"

@@ -7,28 +7,34 @@
 // TF32 pass would not.  Same tiles, A-gather and fused epilogues as
 // gemm_ffma.cuh, so both cores are interchangeable per launch.
 //
-// Persistent, warp-specialised CTA (one per SM), 384 threads (registers re-balanced with setmaxnreg):
-//   warps 0-3  A producers : LDG.128 gather of the (frame x joint x channel) tile rows along
-//                            the channel axis -> hi/lo split -> 128B-swizzled K-major smem
-//   warp  8    B producer  : TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) of the pre-split weights
-//   warp  9    MMA issuer  : one thread issues tcgen05.mma.kind::tf32, accumulators in TMEM
-//   warps 4-7  accumulate  : tcgen05.ld every 32-wide K chunk and add it into fp32 REGISTERS
-//              + epilogue    (round-to-nearest), then smem staging for the joint mixing ->
-//                            bias/BN shift/ReLU/residual | SemCH neighbour mix | attention mix
+// Persistent, warp-specialised CTA (one per SM, 2-CTA clusters share the B tile), 512 threads, registers
+// re-balanced with setmaxnreg (152 / 160 / 40 / 160):
+//   warps 0-3   A converters : raw A rows (TMA or cp.async ring in smem) -> hi/lo split -> tcgen05.st into
+//                              the A ring in TENSOR memory (TS-form MMA)
+//   warp  8     B producer   : TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B, cluster multicast) of the pre-split weights
+//   warp  9     MMA issuer   : one elected thread issues tcgen05.mma.kind::tf32, accumulators in TMEM
+//   warp  10    A producer   : TMA (cp.async.bulk.tensor.3d) of the raw A tile when the frame map is affine
+//   warps 4-7   accumulate + epilogue of accumulator columns 0-63
+//   warps 12-15 accumulate + epilogue of accumulator columns 64-127
+//               tcgen05.ld of every flush group, added into fp32 REGISTERS (round-to-nearest), then smem
+//               staging for the joint mixing -> bias/BN shift/ReLU/residual | SemCH neighbour mix | attention mix
 //
 // Two-level accumulation.  Measured on B200 (tools/tc_probe.py, profiles/r01_tc_numerics.md): the
 // tensor core aligns and TRUNCATES its addends, so a long accumulation chain in TMEM is biased
 // towards zero by ~1 ulp per MMA (K=1536: -1e-5 relative; whole model: 6e-5 abs, MPJPE biased).
-// Therefore the big term A_hi.B_hi is accumulated in TMEM over ONE chunk only (4 MMAs, into a
-// ring of 3 main buffers) and the chunk sums are added in registers with RN; the small terms
+// Therefore the big term A_hi.B_hi is accumulated in TMEM over at most TC_FLUSH chunks (into a ring
+// of 2 main buffers) and the group sums are added in registers with RN; the small terms
 // A_lo.B_hi + A_hi.B_lo (2^-11 of the result, truncation harmless) accumulate over the whole K in
-// a 4th TMEM buffer that is added once per tile.
+// a third TMEM buffer that is added once per tile.
 #pragma once
 #include <cuda.h>
 #include <string.h>
 #include <vector>
 #include "gast_common.cuh"
 
+#ifndef GAST_EXP
+#define GAST_EXP 0
+#endif
 namespace gast {
 
 struct TcWeights {
@@ -48,16 +54,28 @@ constexpr int TC_FLUSH = 4;
 #define GAST_TC_CLUSTER 2
 #endif
 constexpr int TC_CLUSTER = GAST_TC_CLUSTER;   // CTAs per cluster: same N tile, adjacent M tiles, B multicast by TMA     // K chunks accumulated in TMEM before the sum is flushed to registers   // A (activations) ring in TENSOR MEMORY, filled by tcgen05.st
-constexpr int TC_THREADS = 384;   // 3 warpgroups: A producers | accumulate+epilogue | TMA, MMA, 2 idle
+constexpr int TC_THREADS = 512;   // 4 warpgroups: A converters | epilogue (cols 0-63) | TMA, MMA, 1 idle | epilogue (cols 64-127)
+// registers per thread after setmaxnreg: A converters / epilogue groups / TMA+MMA warps (sum x 128 threads <= 64K)
+#ifndef GAST_TC_REG_A
+#define GAST_TC_REG_A 136
+#define GAST_TC_REG_E 168
+#define GAST_TC_REG_M 40
+#endif
+constexpr int TC_REG_A = GAST_TC_REG_A, TC_REG_E = GAST_TC_REG_E, TC_REG_M = GAST_TC_REG_M;
+static_assert(TC_REG_A + 2 * TC_REG_E + TC_REG_M <= 512, "register file over-subscribed");
+constexpr int TC_EN = 64;         // accumulator columns owned by one epilogue warpgroup
 constexpr int TC_STAGE_BYTES = 2 * 16384;            // B_hi, B_lo : 128 rows x 128 B each
 constexpr int TC_SLD = 68;                            // staging row stride (floats): conflict-free 16B rows
 constexpr int TC_MAX_NNZ = 64;    // SemCH coefficient slab rows
-constexpr int TC_COEF_ROWS = 68;   // slab size in rows of TC_SLD floats (also holds the 4 output patches of the global epilogue)
 constexpr int TC_JMAX = 20;
+constexpr int TC_XLD = 36;                            // raw A / 32-column staging row stride (floats): conflict-free row-per-thread access
+// Epilogue scratch, laid out per epilogue kind:
+//   PLAIN : 8 warp-private 32 x TC_XLD patches (two groups x 4 warps)
+//   SEMCH : 2 x [128][TC_XLD] H1 staging (one per group) | coefficient slab [TC_MAX_NNZ][TC_SLD] (64 channels)
+//   GLOBAL: 2 x [128][TC_XLD] g staging (one per group) | a/b tile of group 1 (group 0 uses TC_OFF_AB)
+constexpr int TC_EPI_BYTES = 2 * 128 * TC_XLD * 4 + TC_MAX_NNZ * TC_SLD * 4;
 constexpr int TC_OFF_STAGING = TC_BSTAGES * TC_STAGE_BYTES;
-constexpr int TC_OFF_COEF = TC_OFF_STAGING + 128 * TC_SLD * 4;
-constexpr int TC_OFF_AB = TC_OFF_COEF + TC_COEF_ROWS * TC_SLD * 4;
-constexpr int TC_XLD = 36;                            // raw A row stride (floats): conflict-free row-per-thread reads
+constexpr int TC_OFF_AB = TC_OFF_STAGING + TC_EPI_BYTES;
 constexpr int TC_OFF_XPOSE = (TC_OFF_AB + 128 * 8 * 4 + 1023) / 1024 * 1024;  // raw A ring (1024-aligned: TMA SWIZZLE_128B)
 constexpr int TC_OFF_BAR = TC_OFF_XPOSE + TC_RSTAGES * 128 * TC_XLD * 4;
 static_assert(TC_OFF_STAGING % 1024 == 0 && TC_OFF_XPOSE % 1024 == 0, "swizzled regions must be 1024-byte aligned");
@@ -239,7 +257,8 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// named barrier of one epilogue warpgroup (128 threads): id 1 = columns 0-63, id 2 = columns 64-127
+__device__ __forceinline__ void epi_bar_sync(uint32_t id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row atoms of 1024 B)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -285,7 +304,6 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0) __trap();   // SWIZZLE_128B atoms need 1024-byte alignment
   float* staging = reinterpret_cast<float*>(smem + TC_OFF_STAGING);
-  float* coef_s = reinterpret_cast<float*>(smem + TC_OFF_COEF);
   float* ab_s = reinterpret_cast<float*>(smem + TC_OFF_AB);
   const uint32_t bar0 = sbase + TC_OFF_BAR;
   // mbarriers (8 B each):  b_full[4] @0  b_empty[4] @32  a_full[2] @64  a_empty[2] @80
@@ -319,14 +337,14 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     }
     for (int b = 0; b < (int)NMAIN; ++b) {
       mbar_init(bar0 + BM_FULL + 8 * b, 1);     // tcgen05.commit
-      mbar_init(bar0 + BM_EMPTY + 8 * b, 4);    // 4 accumulate/epilogue warps
+      mbar_init(bar0 + BM_EMPTY + 8 * b, 8);    // 8 accumulate/epilogue warps (two column groups)
     }
     for (int r = 0; r < TC_RSTAGES; ++r) {
       mbar_init(bar0 + BR_FULL + 8 * r, 1);     // raw A slot: expect_tx arrive + TMA bytes
       mbar_init(bar0 + BR_EMPTY + 8 * r, 4);    // 4 A-producer warps have read it
     }
     mbar_init(bar0 + BC_FULL, 1);
-    mbar_init(bar0 + BC_EMPTY, 4);
+    mbar_init(bar0 + BC_EMPTY, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) tmem_alloc(sbase + TC_OFF_BAR + B_TMEMPTR, 512);
@@ -340,7 +358,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
   for (int s = 0; s < p.nseg; ++s) nchunks += p.seg[s].K / TC_BK;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 152;");
+    if (TC_REG_A >= 128) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REG_A)); else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REG_A));
     // ================================================================= A producers
     // Warp w owns tile rows 32w..32w+31 (== its TMEM lane quadrant).  Global loads are COALESCED:
     // instruction i of a chunk covers rows 32w + 4i + (lane>>3), 8 lanes x 16 B = one 128-byte
@@ -488,8 +506,8 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       d[3] = (unsigned long long)(clock64() - tA_tot);
       d[4] = (unsigned long long)tA_ld; d[5] = (unsigned long long)tA_x; d[6] = (unsigned long long)tA_is;
     }
-  } else if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  } else if (warp >= 8 && warp < 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REG_M));
     if (warp == 8) {
     // ================================================================= B producer (TMA)
     if (lane == 0) {
@@ -629,52 +647,63 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    // ================================================================= epilogue warps 4..7
-    const int ew = warp - 4;                 // == warp % 4 : TMEM lane quadrant
-    const int et = tid - 128;                // 0..127
-    const int r = ew * 32 + lane;            // tile row of this thread
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REG_E));
+    // ================================================================= epilogue warps 4..7 and 12..15
+    // Two warpgroups split the tile by COLUMNS: group eh owns accumulator columns [64 eh, 64 eh + 64).
+    // (One group reading all 128 columns needed ~8400 cycles per tile for its tcgen05.ld + epilogue,
+    // 2.7x the MMA time of a K=128 tile: profiles/r01_tc_attribution.md.)  Warp w of either group
+    // reads TMEM lane quadrant w % 4; each group has its own staging area and named barrier.
+    const int eh = (warp >= 12) ? 1 : 0;
+    const int ew = warp & 3;                 // TMEM lane quadrant
+    const int et = ew * 32 + lane;           // 0..127 inside the group
+    const int r = et;                        // tile row of this thread
     const int fr = r / J, ji = r - fr * J;
     const int fb = fr * J;                   // first row of this thread's frame
+    const uint32_t ebar = 1u + (uint32_t)eh; // named barrier of this group
     uint32_t mcount = 0;
     uint32_t tphase = 0;
-    long long tE_n = 0, tE_wait = 0, tE_tot = clock64(), tE_tiles = 0, tE_cw = 0, tE_cl = 0, tE_ep = 0, tE_fl = 0;
-    const uint32_t lane_off = (uint32_t)(ew * 32) << 16;
+    long long tE_n = 0, tE_wait = 0, tE_tot = clock64(), tE_tiles = 0, tE_cw = 0, tE_cl = 0, tE_fl = 0;
+    const uint32_t lane_off = ((uint32_t)(ew * 32) << 16) + (uint32_t)(eh * TC_EN);
+    float* scratch = staging;                // TC_EPI_BYTES, laid out per epilogue kind below
     for (int tile = cid; tile < total_tiles; tile += ncl) {
       const int tn = tile % n_tiles_n;
       const int f0 = tile_f0(tile);
       const int nf = max(0, min(p.fpt, p.F - f0));
       const int vrows = nf * J;
-      const int n0 = tn * TC_BN;
+      const int n0 = tn * TC_BN + eh * TC_EN;          // first output column of this group
       const bool valid = r < vrows;
       const long long orow = (long long)(f0 + fr) * J + ji;
 
       if (EPI == EPI_SEMCH) {
+        // this group's 32 channels of the coefficient slab -> smem (its previous readers are this
+        // group's own warps, past the barrier that ends the loop body)
         const int mask_ = tn / p.tiles_per_mask;
-        const int c0_ = (tn - mask_ * p.tiles_per_mask) * 64;
+        const int c0_ = (tn - mask_ * p.tiles_per_mask) * 64 + eh * 32;
         const int nnz_ = p.nbr[mask_].row_ptr[J];
-        // coefficient slab of this tile's 64 channels -> smem (the previous tile's readers are
-        // done: barrier at the end of the loop body)
-        for (int i = et; i < nnz_ * 16; i += 128) {
-          int z = i >> 4, g = (i & 15) * 4;
+        float* coef_w = scratch + 2 * 128 * TC_XLD + eh * 32;
+        for (int i = et; i < nnz_ * 8; i += 128) {
+          int z = i >> 3, g = (i & 7) * 4;
           float4 cf = make_float4(0.f, 0.f, 0.f, 0.f);
           if (c0_ + g < p.C) cf = ldg4(p.coef[mask_] + (long long)z * p.C + c0_ + g);
-          *reinterpret_cast<float4*>(coef_s + z * TC_SLD + g) = cf;
+          *reinterpret_cast<float4*>(coef_w + z * TC_SLD + g) = cf;
         }
       }
+      float* ab_g = eh ? (scratch + 2 * 128 * TC_XLD) : ab_s;   // per-group copy of the a/b tile
       if (EPI == EPI_GLOBAL) {
         const int H2_ = 2 * p.heads;
         for (int i = et; i < 128 * H2_; i += 128) {
           int rr = i / H2_;
-          ab_s[i] = (rr < vrows) ? __ldg(p.ab + ((long long)f0 * J) * H2_ + i) : 0.f;
+          ab_g[i] = (rr < vrows) ? __ldg(p.ab + ((long long)f0 * J) * H2_ + i) : 0.f;
         }
       }
 
       // ---- level-2 accumulation: group sums (TMEM) -> fp32 registers, round-to-nearest adds.
-      // The first group is loaded straight into the accumulator registers (4 tcgen05.ld in
-      // flight, one wait); later groups go through 2x32 temporaries.
-      float acc[TC_BN];
+      // The first group is loaded straight into the accumulator registers; later groups and the
+      // correction accumulator go through 2x32 temporaries.  (Issuing the correction loads together
+      // with the first group when K is a single flush group made ptxas spill ~175 registers.)
+      float acc[TC_EN];
       const int ngroups = (nchunks + TC_FLUSH - 1) / TC_FLUSH;
+      const bool noflush = (DBG == 1 || DBG == 5);
       {
         const uint32_t mb = mcount % NMAIN;
         long long t0 = 0;
@@ -683,19 +712,15 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         if (DBG == 6) { tE_n += 1; tE_wait += clock64() - t0; t0 = clock64(); }
         tc_fence_after();
         const uint32_t taddr = tmem_base + mb * TC_BN + lane_off;
-        if (DBG == 1 || DBG == 5) {
+        if (noflush) {
 #pragma unroll
-          for (int i = 0; i < TC_BN; ++i) acc[i] = 0.f;
+          for (int i = 0; i < TC_EN; ++i) acc[i] = 0.f;
         } else {
           uint32_t* au = reinterpret_cast<uint32_t*>(acc);
           tmem_ld32_async(taddr, au);
           tmem_ld32_async(taddr + 32, au + 32);
-          tmem_ld32_async(taddr + 64, au + 64);
-          tmem_ld32_async(taddr + 96, au + 96);
           tmem_wait_ld(au);
           tmem_wait_ld(au + 32);
-          tmem_wait_ld(au + 64);
-          tmem_wait_ld(au + 96);
         }
         tc_fence_before();
         __syncwarp();
@@ -711,17 +736,16 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         if (DBG == 6) { tE_n += 1; tE_wait += clock64() - t0; }
         tc_fence_after();
         const uint32_t taddr = tmem_base + mb * TC_BN + lane_off;
-#pragma unroll
-        for (int q = 0; q < ((DBG == 1 || DBG == 5) ? 0 : 4); q += 2) {
+        if (!noflush) {
           uint32_t va[32], vb[32];
-          tmem_ld32_async(taddr + q * 32, va);
-          tmem_ld32_async(taddr + q * 32 + 32, vb);
+          tmem_ld32_async(taddr, va);
+          tmem_ld32_async(taddr + 32, vb);
           tmem_wait_ld(va);
           tmem_wait_ld(vb);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            acc[q * 32 + i] += __uint_as_float(va[i]);
-            acc[q * 32 + 32 + i] += __uint_as_float(vb[i]);
+            acc[i] += __uint_as_float(va[i]);
+            acc[32 + i] += __uint_as_float(vb[i]);
           }
         }
         tc_fence_before();
@@ -736,35 +760,35 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         if (DBG == 6) { long long t1 = clock64(); tE_cw += t1 - tc0; tc0 = t1; }
         tc_fence_after();
         const uint32_t taddr = tmem_base + CORR_COL + lane_off;
-#pragma unroll
-        for (int q = 0; q < ((DBG == 1 || DBG == 5) ? 0 : 4); q += 2) {
+        if (!noflush) {
           uint32_t va[32], vb[32];
-          tmem_ld32_async(taddr + q * 32, va);
-          tmem_ld32_async(taddr + q * 32 + 32, vb);
+          tmem_ld32_async(taddr, va);
+          tmem_ld32_async(taddr + 32, vb);
           tmem_wait_ld(va);
           tmem_wait_ld(vb);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            acc[q * 32 + i] += __uint_as_float(va[i]);
-            acc[q * 32 + 32 + i] += __uint_as_float(vb[i]);
+            acc[i] += __uint_as_float(va[i]);
+            acc[32 + i] += __uint_as_float(vb[i]);
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar0 + BC_EMPTY);
-        tphase ^= 1;
-        if (DBG == 6) { long long t1 = clock64(); tE_cl += t1 - tc0; tc0 = t1; ++tE_tiles; }
+        if (DBG == 6) { long long t1 = clock64(); tE_cl += t1 - tc0; tc0 = t1; }
       }
+      tphase ^= 1;
+      if (DBG == 6) ++tE_tiles;
 
       if (EPI == EPI_PLAIN) {
         // Row-per-thread registers -> warp-private smem patch -> COALESCED 128-bit stores (8 lanes
         // cover one 128-byte row segment).  Storing straight from the row-per-thread layout issues
         // 32 half-sector writes per instruction: clock64 attribution showed ~7500 of the ~8000
         // epilogue cycles of a tile in those stores (profiles/r01_tc_attribution.md).
-        float* patch = staging + ew * (32 * TC_XLD);
+        float* patch = scratch + (eh * 4 + ew) * (32 * TC_XLD);
         const int rsub = lane >> 3, ch = lane & 7;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
           const int nq = n0 + q * 32;
           if (nq < p.N) {                       // warp-uniform
 #pragma unroll
@@ -796,21 +820,25 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           }
         }
       } else if (EPI == EPI_SEMCH) {
+        // Weight rows are interleaved per 32 channels (tc_split_kernel, semch order): this group's
+        // 64 columns are  acc[0..31] = X.W0 (self term), acc[32..63] = X.W1 (neighbour term)  of
+        // channels c0 .. c0+31.
         const int mask = tn / p.tiles_per_mask;
-        const int c0 = (tn - mask * p.tiles_per_mask) * 64;
+        const int c0 = (tn - mask * p.tiles_per_mask) * 64 + eh * 32;
         const NbrTable& nb = p.nbr[mask];
-        // acc[0..63] = X.W0 (self term), acc[64..127] = X.W1 (neighbour term) -> staging
+        float* Hs = scratch + eh * (128 * TC_XLD);               // [128 rows][32 ch], stride TC_XLD
+        const float* coef_r = scratch + 2 * 128 * TC_XLD + eh * 32;
 #pragma unroll
-        for (int g = 0; g < 16; ++g)
-          *reinterpret_cast<float4*>(staging + r * TC_SLD + g * 4) =
-              make_float4(acc[64 + g * 4], acc[64 + g * 4 + 1], acc[64 + g * 4 + 2], acc[64 + g * 4 + 3]);
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(Hs + r * TC_XLD + g * 4) =
+              make_float4(acc[32 + g * 4], acc[32 + g * 4 + 1], acc[32 + g * 4 + 2], acc[32 + g * 4 + 3]);
         const float* h0 = acc;
-        epi_bar_sync();
-        float ov[64];
+        epi_bar_sync(ebar);
+        float ov[32];
         {
           const int z0 = valid ? nb.row_ptr[ji] : 0, z1 = valid ? nb.row_ptr[ji + 1] : 0;
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq) {           // 16 channels at a time
+          for (int gq = 0; gq < 2; ++gq) {           // 16 channels at a time
             float o[16];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -821,8 +849,8 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
             }
             for (int z = z0; z < z1; ++z) {
               const int jn = nb.col[z];
-              const float* hrow = staging + (fb + jn) * TC_SLD + gq * 16;
-              const float* crow = coef_s + z * TC_SLD + gq * 16;
+              const float* hrow = Hs + (fb + jn) * TC_XLD + gq * 16;
+              const float* crow = coef_r + z * TC_SLD + gq * 16;
               const bool self = (jn == ji);
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
@@ -837,89 +865,95 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
             for (int g = 0; g < 16; ++g) ov[gq * 16 + g] = p.relu ? fmaxf(o[g], 0.f) : o[g];
           }
         }
-        epi_bar_sync();      // every neighbour read of the staged H1 tile is done: reuse it for the output
+        epi_bar_sync(ebar);  // every neighbour read of the staged H1 tile is done: reuse it for the output
 #pragma unroll
-        for (int g = 0; g < 16; ++g)
-          *reinterpret_cast<float4*>(staging + r * TC_SLD + g * 4) =
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(Hs + r * TC_XLD + g * 4) =
               make_float4(ov[g * 4], ov[g * 4 + 1], ov[g * 4 + 2], ov[g * 4 + 3]);
         __syncwarp();
         {
-          // coalesced: 16 lanes cover the 256-byte row segment of one row, 2 rows per instruction
-          const int rs = lane >> 4, chq = lane & 15;
+          // coalesced: 8 lanes cover the 128-byte row segment of one row, 4 rows per instruction
+          const int rs = lane >> 3, chq = lane & 7;
           const int c = c0 + chq * 4;
 #pragma unroll 4
-          for (int i = 0; i < 16; ++i) {
-            const int rr = ew * 32 + 2 * i + rs;
+          for (int i = 0; i < 8; ++i) {
+            const int rr = ew * 32 + 4 * i + rs;
             if (rr < vrows && c < p.C)
               *reinterpret_cast<float4*>(p.out + ((long long)f0 * J + rr) * p.ld_out + mask * p.C + c) =
-                  *reinterpret_cast<const float4*>(staging + rr * TC_SLD + chq * 4);
+                  *reinterpret_cast<const float4*>(Hs + rr * TC_XLD + chq * 4);
           }
         }
-        epi_bar_sync();      // staging / coef slab free for the next tile
+        epi_bar_sync(ebar);  // staging / coefficient slab free for the next tile
       } else {               // EPI_GLOBAL
         const int H2 = 2 * p.heads;
+        float* Gs = scratch + eh * (128 * TC_XLD);               // [128 rows][32 cols], stride TC_XLD
+        float att[TC_JMAX];                                      // attention row of (this joint, head att_h)
+        int att_h = -1;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int nb0 = n0 + half * 64;
+        for (int ps = 0; ps < 2; ++ps) {
+          const int nb0 = n0 + ps * 32;
 #pragma unroll
-          for (int g = 0; g < 16; ++g) {
+          for (int g = 0; g < 8; ++g) {
             const int n = nb0 + g * 4;
             float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bg && n < p.N) bb = ldg4(p.bg + n);
-            *reinterpret_cast<float4*>(staging + r * TC_SLD + g * 4) =
-                make_float4(acc[half * 64 + g * 4] + bb.x, acc[half * 64 + g * 4 + 1] + bb.y,
-                            acc[half * 64 + g * 4 + 2] + bb.z, acc[half * 64 + g * 4 + 3] + bb.w);
+            *reinterpret_cast<float4*>(Gs + r * TC_XLD + g * 4) =
+                make_float4(acc[ps * 32 + g * 4] + bb.x, acc[ps * 32 + g * 4 + 1] + bb.y,
+                            acc[ps * 32 + g * 4 + 2] + bb.z, acc[ps * 32 + g * 4 + 3] + bb.w);
           }
-          epi_bar_sync();
+          epi_bar_sync(ebar);
           // (a register/patch-staged, coalesced-store variant of this mix measured 70 % slower than the
           //  direct row-per-thread stores below: profiles/r01_tc_attribution.md)
-          if (valid && nb0 < p.N) {
-            const int nend = min(nb0 + 64, p.N);
+          if (valid && nb0 < p.N && GAST_EXP != 1) {
+            const int nend = min(nb0 + 32, p.N);
             const int h_lo = nb0 / p.Cg, h_hi = (nend - 1) / p.Cg;
             for (int h = h_lo; h <= h_hi; ++h) {
-              // attention row of joint ji: softmax_j(LeakyReLU_0.2(a_i + b_j)) + C_k[i,j]
-              float att[TC_JMAX];
-              const float a = ab_s[r * H2 + 2 * h];
-              float mx = -3.4e38f;
-#pragma unroll
-              for (int j = 0; j < TC_JMAX; ++j) {
-                if (j < J) {
-                  float s = a + ab_s[(fb + j) * H2 + 2 * h + 1];
-                  s = (s >= 0.f) ? s : 0.2f * s;
-                  att[j] = s;
-                  mx = fmaxf(mx, s);
-                }
-              }
-              float sum = 0.f;
-#pragma unroll
-              for (int j = 0; j < TC_JMAX; ++j)
-                if (j < J) { att[j] = expf(att[j] - mx); sum += att[j]; }
-              const float inv = 1.f / sum;
-              const float* ck = p.ck + ((long long)h * J + ji) * J;
-#pragma unroll
-              for (int j = 0; j < TC_JMAX; ++j)
-                if (j < J) att[j] = att[j] * inv + __ldg(ck + j);
-              const int cbeg = max(h * p.Cg, nb0), cend = min((h + 1) * p.Cg, nend);
-              for (int n = cbeg; n < cend; n += 4) {
-                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                const float* scol = staging + fb * TC_SLD + (n - nb0);
+              // attention row of joint ji: softmax_j(LeakyReLU_0.2(a_i + b_j)) + C_k[i,j]; kept across the
+              // two 32-column passes when they belong to the same head (Cg >= 64)
+              if (h != att_h) {
+                att_h = h;
+                const float a = ab_g[r * H2 + 2 * h];
+                float mx = -3.4e38f;
 #pragma unroll
                 for (int j = 0; j < TC_JMAX; ++j) {
                   if (j < J) {
-                    float4 g4 = *reinterpret_cast<const float4*>(scol + j * TC_SLD);
+                    float s = a + ab_g[(fb + j) * H2 + 2 * h + 1];
+                    s = (s >= 0.f) ? s : 0.2f * s;
+                    att[j] = s;
+                    mx = fmaxf(mx, s);
+                  }
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < TC_JMAX; ++j)
+                  if (j < J) { att[j] = expf(att[j] - mx); sum += att[j]; }
+                const float inv = 1.f / sum;
+                const float* ck = p.ck + ((long long)h * J + ji) * J;
+#pragma unroll
+                for (int j = 0; j < TC_JMAX; ++j)
+                  if (j < J) att[j] = att[j] * inv + __ldg(ck + j);
+              }
+              const int cbeg = max(h * p.Cg, nb0), cend = min((h + 1) * p.Cg, nend);
+              for (int n = cbeg; n < cend; n += 4) {
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float* scol = Gs + fb * TC_XLD + (n - nb0);
+#pragma unroll
+                for (int j = 0; j < TC_JMAX; ++j) {
+                  if (j < J) {
+                    float4 g4 = *reinterpret_cast<const float4*>(scol + j * TC_XLD);
                     o.x = fmaf(att[j], g4.x, o.x); o.y = fmaf(att[j], g4.y, o.y);
                     o.z = fmaf(att[j], g4.z, o.z); o.w = fmaf(att[j], g4.w, o.w);
                   }
                 }
-                *reinterpret_cast<float4*>(p.out + orow * p.ld_out + n) = o;
+                if (GAST_EXP != 3 || o.x == 12345.678f) *reinterpret_cast<float4*>(p.out + orow * p.ld_out + n) = o;
               }
             }
           }
-          epi_bar_sync();    // staging free for the next half / tile
+          epi_bar_sync(ebar);  // staging (and, after the last pass, the a/b tile) free for reuse
         }
       }
     }
-    if (DBG == 6 && et == 0 && p.dbg) {
+    if (DBG == 6 && et == 0 && eh == 0 && p.dbg) {
       p.dbg[(size_t)blockIdx.x * 32 + 27] = (unsigned long long)tE_tiles;
       p.dbg[(size_t)blockIdx.x * 32 + 28] = (unsigned long long)tE_cw;
       p.dbg[(size_t)blockIdx.x * 32 + 29] = (unsigned long long)tE_cl;
@@ -950,11 +984,21 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
 // within W_lo's own rounding budget).
 constexpr float TC_TRUNC_C = 3.5e-8f;
 
+// semch != 0: W is the SemCH packing of gast_api.cu ([W0 of 64 channels | W1 of the same 64] per
+// 128-row tile); the copies interleave it per 32 channels ([W0 32 | W1 32 | W0 next 32 | W1 next 32]) so
+// that each epilogue warpgroup (64 accumulator columns) holds self and neighbour terms of the same channels.
 __global__ void tc_split_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo,
-                                long long n, int K) {
+                                long long n, int K, int semch) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float x = w[i];
+  long long src = i;
+  if (semch) {
+    const long long row = i / K;
+    const int within = (int)(row & 127), half = within >> 6, sub = within & 63;
+    const int srow = (sub >> 5) * 64 + half * 32 + (sub & 31);
+    src = ((row & ~127LL) + srow) * K + (i - row * K);
+  }
+  float x = w[src];
   float h = tf32_rna(x);
   const int k = (int)(i % K);
   const int nchunks = K / TC_BK;
@@ -985,7 +1029,7 @@ inline tc_encode_fn tc_get_encode() {
 // W: [N][K] fp32 K-major (device).  Allocates hi/lo once, splits, encodes the TMA maps.
 // Returns 0 on success, a cudaError_t / -1 otherwise.
 inline int tc_prepare_weights(TcWeights& t, const float* W, int N, int K, cudaStream_t st,
-                              std::vector<void*>* owned) {
+                              std::vector<void*>* owned, int semch = 0) {
   t.ready = false;
   if (K % TC_BK != 0 || N % 4 != 0) return 0;            // shape not taken by this core (FFMA runs it)
   tc_encode_fn enc = tc_get_encode();
@@ -1011,7 +1055,8 @@ inline int tc_prepare_weights(TcWeights& t, const float* W, int N, int K, cudaSt
     if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return -1;
   }
   long long n = (long long)N * K;
-  tc_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, t.hi, t.lo, n, K);
+  if (semch && N % 128) return -1;
+  tc_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, t.hi, t.lo, n, K, semch);
   t.ready = true;
   return 0;
 }

@@ -18,7 +18,10 @@ SYMBOLS = ['gast_create', 'gast_destroy', 'gast_bind', 'gast_prepare', 'gast_out
            'gast_receptive_field', 'gast_workspace_bytes', 'gast_forward',
            'gast_last_launch_count', 'gast_last_tc_launch_count', 'gast_set_timing',
            'gast_get_timings', 'gast_set_gemm_core', 'gast_debug_gemm', 'gast_bind_grads',
-           'gast_train_workspace_bytes', 'gast_forward_train', 'gast_backward', 'gast_tta_prepare', 'gast_tta_merge', 'gast_last_error', 'gast_version']
+           'gast_train_workspace_bytes', 'gast_forward_train', 'gast_backward', 'gast_tta_prepare', 'gast_tta_merge',
+           'gast_chunk_gather', 'gast_keypoints_convert', 'gast_normalize_screen', 'gast_camera_to_world',
+           'gast_mpjpe_workspace_bytes', 'gast_mpjpe', 'gast_p_mpjpe', 'gast_adam_chunk', 'gast_adam_step',
+           'gast_last_error', 'gast_version']
 
 
 class GastCfg(C.Structure):
@@ -91,6 +94,28 @@ def load():
     lib.gast_tta_prepare.restype = C.c_int
     lib.gast_tta_merge.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, ip, ip, vp]
     lib.gast_tta_merge.restype = C.c_int
+    fp = C.POINTER(C.c_float)
+    lib.gast_chunk_gather.argtypes = [vp, vp, vp, vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, ip, ip, C.c_int32, ip, ip,
+                                      vp, vp, vp, vp]
+    lib.gast_chunk_gather.restype = C.c_int
+    lib.gast_keypoints_convert.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
+    lib.gast_keypoints_convert.restype = C.c_int
+    lib.gast_normalize_screen.argtypes = [vp, vp, C.c_int64, C.c_float, C.c_float, C.c_int32, vp]
+    lib.gast_normalize_screen.restype = C.c_int
+    lib.gast_camera_to_world.argtypes = [vp, vp, C.c_int64, fp, fp, vp]
+    lib.gast_camera_to_world.restype = C.c_int
+    lib.gast_mpjpe_workspace_bytes.argtypes = []
+    lib.gast_mpjpe_workspace_bytes.restype = C.c_size_t
+    lib.gast_mpjpe.argtypes = [vp, vp, C.c_int64, C.c_int32, vp, vp, C.c_float, vp, vp]
+    lib.gast_mpjpe.restype = C.c_int
+    lib.gast_p_mpjpe.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp]
+    lib.gast_p_mpjpe.restype = C.c_int
+    lib.gast_adam_chunk.argtypes = []
+    lib.gast_adam_chunk.restype = C.c_int32
+    lib.gast_adam_step.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double,
+                                   C.c_double, C.c_int64, vp]
+    lib.gast_adam_step.restype = C.c_int
     lib.gast_last_error.argtypes = []
     lib.gast_last_error.restype = C.c_char_p
     lib.gast_version.argtypes = []

@@ -142,6 +142,53 @@ int gast_forward_train(gast_t* h, const float* x, float* y, int32_t B, int32_t T
                        void* workspace, size_t workspace_bytes, void* stream);
 int gast_backward(gast_t* h, const float* dy, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- either side of the forward, on the device --------------------------------
+ * All pointers are device pointers unless marked (host).  Work is enqueued on `stream`.
+ *
+ * gast_chunk_gather: one training batch of ChunkedGenerator.next_epoch (common/generators.py:93-154).
+ *   poses_2d (total_frames,J2,F2) / poses_3d (total_frames,J3,3) = every sequence concatenated along
+ *   time; seq_start[n_seq+1] = first frame of each sequence; cameras (n_seq,ncam); pairs (B,4) int32 =
+ *   the reference's (seq_i, start_3d, end_3d, flip) tuples.  Writes batch_2d (B,chunk+2*pad,J2,F2)
+ *   with edge padding and the horizontal flip (:107-121), batch_3d (B,chunk,J3,3) (:123-135, may be
+ *   null) and batch_cam (B,ncam) (:137-144, may be null).  kps_/joints_ lists: (host). */
+int gast_chunk_gather(const float* poses_2d, const float* poses_3d, const float* cameras, const int64_t* seq_start,
+                      int32_t n_seq, const int32_t* pairs, int32_t B, int32_t chunk, int32_t pad, int32_t causal_shift,
+                      int32_t J2, int32_t F2, int32_t J3, int32_t ncam, int32_t n_sym2, const int32_t* kps_left,
+                      const int32_t* kps_right, int32_t n_sym3, const int32_t* joints_left, const int32_t* joints_right,
+                      float* batch_2d, float* batch_3d, float* batch_cam, void* stream);
+
+/* tools/mpii_coco_h36m.py: mode 0 = coco_h36m (T,17,2)->(T,17,2) (:20-48), 1 = mpii_h36m (T,16,2)->(T,17,2)
+ * (:51-59), 2 = coco_h36m_toe_format (T,J_in>=22,2)->(T,19,2) (:62-78).  valid (T) int32, may be null:
+ * 1 where the frame's coordinate sum is non-zero (the mask the reference takes np.where of). */
+int gast_keypoints_convert(const float* kpts, float* out, int32_t* valid, int32_t T, int32_t J_in, int32_t mode,
+                           void* stream);
+
+/* common/camera.py:8-19: normalize_screen_coordinates (inverse = 0) / image_coordinates (inverse = 1) on
+ * n_points (x,y) pairs. */
+int gast_normalize_screen(const float* x, float* out, int64_t n_points, float w, float h, int32_t inverse, void* stream);
+
+/* common/camera.py:27-28 camera_to_world with one rotation for all points: qort(q, x) + t
+ * (common/quaternion.py:4-18).  q[4], t[3] (host; t may be null = 0). */
+int gast_camera_to_world(const float* x, float* out, int64_t n_points, const float* q, const float* t, void* stream);
+
+/* common/loss.py:5-11 mpjpe: *loss = mean_i ||pred_i - target_i|| over n_points rows of D (<= 4) coordinates;
+ * when dpred is not null it receives grad_scale * d loss / d pred (the backward of the same pass).
+ * workspace: gast_mpjpe_workspace_bytes() bytes of scratch. */
+size_t gast_mpjpe_workspace_bytes(void);
+int gast_mpjpe(const float* pred, const float* target, int64_t n_points, int32_t D, float* loss, float* dpred,
+               float grad_scale, void* workspace, void* stream);
+
+/* common/loss.py:14-53 p_mpjpe: per_frame[n] = mean joint distance of frame n after the similarity
+ * (Procrustes) alignment of pred[n] (J,3) to target[n]; the reference's scalar is the mean of per_frame. */
+int gast_p_mpjpe(const float* pred, const float* target, int32_t N, int32_t J, float* per_frame, void* stream);
+
+/* optim.Adam(amsgrad=True) (trainval.py:78,162-164) for every parameter in one launch.  table (n_chunks,4)
+ * int64 on the device: {param pointer, grad pointer, offset into the flat state buffers, count <=
+ * gast_adam_chunk()}.  max_exp_avg_sq null = plain Adam.  step = 1 for the first update. */
+int32_t gast_adam_chunk(void);
+int gast_adam_step(const int64_t* table, int32_t n_chunks, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq,
+                   double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step, void* stream);
+
 /* Test/probe entry (not on the forward path): out[M,N] = A[M,K] . W[N,K]^T on one GEMM core
  * (core 0 = tcgen05 3xTF32, 1 = FFMA).  tc_mode != 0 selects a timing-experiment variant of the
  * tcgen05 kernel (parts disabled; results invalid).  Runs once, then `reps` timed launches

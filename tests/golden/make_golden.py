@@ -115,6 +115,93 @@ def tta_cases():
     print('tta_17', {k: v.shape for k, v in out.items()})
 
 
+def pipeline_cases():
+    """N1-N3 goldens: the reference's own ChunkedGenerator, keypoint converters, screen
+    normalisation, camera_to_world, mpjpe (+ autograd), p_mpjpe and torch.optim.Adam(amsgrad=True).
+    Inputs are re-created in the tests from the seeds below; only outputs (and small inputs) are stored."""
+    from common.generators import ChunkedGenerator
+    from common.loss import mpjpe, p_mpjpe
+    from common.camera import normalize_screen_coordinates, image_coordinates, camera_to_world
+    from tools.mpii_coco_h36m import coco_h36m, mpii_h36m, coco_h36m_toe_format
+    import tools.mpii_coco_h36m as _kc
+    assert _kc.__file__.startswith(REF)
+    out = {}
+    left, right = [4, 5, 6, 11, 12, 13], [1, 2, 3, 14, 15, 16]
+    # --- ChunkedGenerator: 3 videos, augment + shuffle, 27-frame receptive field; and a causal, unshuffled one
+    rs = np.random.RandomState(21)
+    lens = (40, 7, 25)
+    p2 = [rs.standard_normal((n, 17, 2)).astype(np.float32) for n in lens]
+    p3 = [rs.standard_normal((n, 17, 3)).astype(np.float32) for n in lens]
+    cams = [rs.standard_normal(9).astype(np.float32) for _ in lens]
+    gen = ChunkedGenerator(8, cams, p3, p2, 1, pad=13, causal_shift=0, shuffle=True, random_seed=1234, augment=True,
+                           kps_left=left, kps_right=right, joints_left=left, joints_right=right)
+    with torch.enable_grad():
+        pass
+    for bi, (cam, b3, b2) in enumerate(gen.next_epoch()):
+        if bi in (0, 1, gen.num_batches - 1):
+            out['cg_a%d_cam' % bi] = cam.astype(np.float32).copy()
+            out['cg_a%d_3d' % bi] = b3.astype(np.float32).copy()
+            out['cg_a%d_2d' % bi] = b2.astype(np.float32).copy()
+    out['cg_a_num_batches'] = np.array(gen.num_batches)
+    gen = ChunkedGenerator(5, None, p3, p2, 3, pad=4, causal_shift=4, shuffle=False, augment=False)
+    for bi, (cam, b3, b2) in enumerate(gen.next_epoch()):
+        assert cam is None
+        if bi in (0, gen.num_batches - 1):
+            out['cg_b%d_3d' % bi] = b3.astype(np.float32).copy()
+            out['cg_b%d_2d' % bi] = b2.astype(np.float32).copy()
+    out['cg_b_num_batches'] = np.array(gen.num_batches)
+    # --- keypoint formats (float32 pixel coordinates; one all-zero frame -> not in valid_frames)
+    rs = np.random.RandomState(22)
+    k17 = (rs.uniform(0, 1000, (12, 17, 2))).astype(np.float32); k17[5] = 0
+    k16 = (rs.uniform(0, 1000, (9, 16, 2))).astype(np.float32); k16[2] = 0
+    k133 = (rs.uniform(0, 1000, (7, 133, 2))).astype(np.float32); k133[3] = 0
+    out['k17'], out['k16'], out['k133'] = k17, k16, k133
+    out['coco_h36m'], out['coco_h36m_valid'] = coco_h36m(k17.copy())
+    out['mpii_h36m'], out['mpii_h36m_valid'] = mpii_h36m(k16.copy())
+    out['coco_toe'], out['coco_toe_valid'] = coco_h36m_toe_format(k133.copy())
+    # --- screen normalisation / camera_to_world (reconstruction.py:143,204 call forms)
+    out['norm_screen'] = normalize_screen_coordinates(k17[..., :2].copy(), w=1920, h=1080).astype(np.float32)
+    out['img_coords'] = image_coordinates(out['norm_screen'].copy(), w=1920, h=1080).astype(np.float32)
+    rot = np.array([0.1407056450843811, -0.1500701755285263, -0.755240797996521, 0.6223280429840088], dtype=np.float32)
+    x3 = rs.standard_normal((11, 17, 3)).astype(np.float32)
+    out['x3'] = x3
+    out['rot'] = rot
+    out['cam2world'] = camera_to_world(x3.copy(), R=rot, t=0).astype(np.float32)
+    # --- mpjpe + gradient, p_mpjpe
+    pr = torch.from_numpy(rs.standard_normal((6, 1, 17, 3)).astype(np.float32)).requires_grad_(True)
+    tg = torch.from_numpy(rs.standard_normal((6, 1, 17, 3)).astype(np.float32))
+    tg.data[0, 0, 3] = pr.data[0, 0, 3]                       # a zero-distance joint (gradient 0 there)
+    with torch.enable_grad():
+        l = mpjpe(pr, tg)
+        l.backward()
+    out['mp_pred'], out['mp_tgt'] = pr.detach().numpy().copy(), tg.numpy().copy()
+    out['mp_loss'], out['mp_grad'] = np.array(l.item(), np.float32), pr.grad.numpy().copy()
+    pp = rs.standard_normal((7, 17, 3)).astype(np.float32)
+    pt = (pp * 1.7 + 0.3 * rs.standard_normal((7, 17, 3))).astype(np.float32)
+    pt[2, :, 0] *= -1                                           # a mirrored target: the det(R) = -1 branch
+    pp[4, :, 2] = 0.0                                           # a planar prediction: rank-deficient H
+    out['pm_pred'], out['pm_tgt'] = pp, pt
+    out['pm_value'] = np.array(p_mpjpe(pp.copy(), pt.copy()), np.float64)
+    out['pm_per_frame'] = np.array([p_mpjpe(pp[i:i + 1].copy(), pt[i:i + 1].copy()) for i in range(7)], np.float64)
+    # --- Adam(amsgrad=True), 4 steps with a learning-rate decay in between (trainval.py:78,162-164)
+    shapes = [(5000,), (33, 7), (1,)]
+    ps = [torch.nn.Parameter(torch.from_numpy(rs.standard_normal(sh).astype(np.float32))) for sh in shapes]
+    opt = torch.optim.Adam(ps, lr=1e-3, amsgrad=True)
+    grads = []
+    for step in range(4):
+        gs = [rs.standard_normal(sh).astype(np.float32) * (10.0 if step == 1 else 0.1) for sh in shapes]
+        grads.append(gs)
+        for p_, g_ in zip(ps, gs):
+            p_.grad = torch.from_numpy(g_.copy())
+        opt.step()
+        for g in opt.param_groups:
+            g['lr'] *= 0.95
+    for i, p_ in enumerate(ps):
+        out['adam_p%d' % i] = p_.detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, 'pipeline_17.npz'), **out)
+    print('pipeline_17', {k: getattr(v, 'shape', None) for k, v in out.items()})
+
+
 def module_cases():
     J, C = 17, 32
     adj = adj_for(J)
@@ -191,6 +278,9 @@ def main():
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'tta':
         tta_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'pipeline':
+        pipeline_cases()
     else:
         main()
         tta_cases()
+        pipeline_cases()

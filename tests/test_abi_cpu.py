@@ -79,3 +79,22 @@ def test_skeleton_remove_joints_like_reference():
     got[14] = 8                                   # shoulder rewiring, h36m_dataset.py:284-285
     assert got == synth.H36M_PARENTS_17
     assert sk.joints_left() == [4, 5, 6, 11, 12, 13] and sk.joints_right() == [1, 2, 3, 14, 15, 16]
+
+
+def test_reference_checkpoint_layout_loads(tmp_path):
+    """N4: a checkpoint in the reference's on-disk layout ({'model_pos': state_dict}, trainval.py:192-199),
+    also with the `module.` prefixes an nn.DataParallel-wrapped model writes, loads strictly."""
+    from model.gast_net import SpatioTemporalModel
+    from gast_b200.checkpoint import load_checkpoint
+    src = SpatioTemporalModel(_adj(17), 17, 2, 17, [3, 3, 3], channels=16)
+    synth.randomize_module(src, 4)
+    for prefix in ('', 'module.'):
+        path = os.path.join(str(tmp_path), 'm%d.bin' % len(prefix))
+        torch.save({'epoch': 3, 'lr': 1e-3, 'model_pos': {prefix + k: v for k, v in src.state_dict().items()}}, path)
+        dst = SpatioTemporalModel(_adj(17), 17, 2, 17, [3, 3, 3], channels=16)
+        chk = load_checkpoint(dst, path)
+        assert chk['epoch'] == 3
+        for (k, a), (_, b) in zip(src.state_dict().items(), dst.state_dict().items()):
+            assert torch.equal(a, b), k
+    plain = SpatioTemporalModel(_adj(17), 17, 2, 17, [3, 3, 3], channels=16)
+    plain.load_state_dict(torch.load(path.replace('m7', 'm0'))['model_pos'])      # reconstruction.py:239-240 verbatim
