@@ -555,6 +555,13 @@ static void gemm_defaults(GemmP& p, const gast_handle* h, long long F) {
   p.res_map = RowMap{1, 1, 1, 0};
 }
 
+// A 1x1 layer with flat operands and no joint mixing does not need frame-aligned tiles: run it as
+// F*J "frames" of one joint, so that every tile carries 128 rows instead of floor(128/J)*J (119 for J=17).
+static void gemm_defaults_flat(GemmP& p, const gast_handle* h, long long F) {
+  gemm_defaults(p, h, F);
+  p.F = (int)(F * h->cfg.num_joints); p.J = 1; p.fpt = 128;
+}
+
 static int launch_gemm(gast_handle* h, cudaStream_t st, int epi, const GemmP& p, const TcWeights* tcw) {
   if (p.F <= 0) return 0;
   int Ktot = 0;
@@ -624,7 +631,7 @@ static int run_local(gast_handle* h, cudaStream_t st, BlockConsts& b, const floa
   p.nbr[0] = h->nbr[0]; p.nbr[1] = h->nbr[1];
   if (launch_gemm(h, st, EPI_SEMCH, p, &b.tc_loc)) return 1;
   if (kind == GAST_KIND_SEMCH) return 0;
-  gemm_defaults(p, h, F);
+  gemm_defaults_flat(p, h, F);
   p.nseg = 1; p.seg[0] = seg_flat(w.XY, 2 * C, 2 * C);
   p.W = b.Wlc; p.ldw = 2 * C; p.N = C; p.out = out_L; p.ld_out = C; p.bias = b.blc; p.relu = 1;
   return launch_gemm(h, st, EPI_PLAIN, p, &b.tc_lc);
@@ -644,7 +651,7 @@ static int run_global(gast_handle* h, cudaStream_t st, BlockConsts& b, const flo
   p.ab = w.AB; p.ck = b.Ck; p.bg = b.bg; p.heads = b.heads; p.Cg = b.Cg;
   if (launch_gemm(h, st, EPI_GLOBAL, p, &b.tc_g)) return 1;
   if (kind == GAST_KIND_GLOBAL_HEAD) return 0;
-  gemm_defaults(p, h, F);
+  gemm_defaults_flat(p, h, F);
   p.nseg = 1; p.seg[0] = seg_flat(w.Y, C, C);
   p.W = b.Wgc; p.ldw = C; p.N = C; p.out = out_G; p.ld_out = C; p.bias = b.bgc; p.relu = 1;
   return launch_gemm(h, st, EPI_PLAIN, p, &b.tc_gc);
@@ -657,7 +664,7 @@ static int run_block(gast_handle* h, cudaStream_t st, BlockConsts& b, const floa
   if (run_local(h, st, b, X, F, w, w.L, GAST_KIND_BLOCK)) return 1;
   if (run_global(h, st, b, X, F, w, w.Gl, GAST_KIND_BLOCK)) return 1;
   GemmP p;
-  gemm_defaults(p, h, F);
+  gemm_defaults_flat(p, h, F);
   p.nseg = 3;
   p.seg[0] = seg_flat(X, C, C); p.seg[1] = seg_flat(w.L, C, C); p.seg[2] = seg_flat(w.Gl, C, C);
   p.W = b.Wbc; p.ldw = 3 * C; p.N = 2 * C; p.out = out; p.ld_out = 2 * C; p.bias = b.bbc; p.relu = 1;

@@ -32,9 +32,6 @@
 #include <vector>
 #include "gast_common.cuh"
 
-#ifndef GAST_EXP
-#define GAST_EXP 0
-#endif
 namespace gast {
 
 struct TcWeights {
@@ -787,31 +784,53 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         // epilogue cycles of a tile in those stores (profiles/r01_tc_attribution.md).
         float* patch = scratch + (eh * 4 + ew) * (32 * TC_XLD);
         const int rsub = lane >> 3, ch = lane & 7;
+        // Residual rows of the 8 tile rows this lane stores (stage 1x1 convs, gast_net.py:174): ONE 32-bit
+        // division per tile -- the frames of a tile are consecutive.  (map_frame()'s 64-bit divisions per
+        // stored float4 made the residual GEMMs 2.5x slower than their MMA time.)
+        unsigned rres[8];                        // residual row offsets in 16-byte units (res_ld % 4 == 0)
+        if (p.res) {
+          const int b0 = f0 / p.res_map.T_out, t0 = f0 - b0 * p.res_map.T_out;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = ew * 32 + 4 * i + rsub;
+            const int frr = rr / J, jr = rr - frr * J;
+            int b = b0, t = t0 + frr;
+            while (t >= p.res_map.T_out) { t -= p.res_map.T_out; ++b; }
+            rres[i] = (unsigned)(((((long long)b * p.res_map.T_in + (long long)t * p.res_map.t_mul + p.res_map.t_off) * J + jr) *
+                                  (long long)p.res_ld) >> 2);
+          }
+        }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int nq = n0 + q * 32;
           if (nq < p.N) {                       // warp-uniform
+            const int n = nq + ch * 4;
+            // residual values of this lane's 8 stores: all 8 loads in flight BEFORE the patch round trip
+            // (one exposed HBM latency per 32 columns instead of one per stored float4)
+            float4 rv[8];
+            if (p.res) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rr = ew * 32 + 4 * i + rsub;
+                rv[i] = (rr < vrows && n < p.N) ? ldg4(p.res + 4ull * rres[i] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-              const int n = nq + g * 4;
+              const int nn = nq + g * 4;
               float4 o = make_float4(acc[q * 32 + g * 4], acc[q * 32 + g * 4 + 1], acc[q * 32 + g * 4 + 2],
                                      acc[q * 32 + g * 4 + 3]);
-              if (p.bias && n < p.N) { float4 bb = ldg4(p.bias + n); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
+              if (p.bias && nn < p.N) { float4 bb = ldg4(p.bias + nn); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
               if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
               *reinterpret_cast<float4*>(patch + lane * TC_XLD + g * 4) = o;
             }
             __syncwarp();
-            const int n = nq + ch * 4;
-#pragma unroll 2
+#pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = ew * 32 + 4 * i + rsub;          // tile row stored by this lane
               if (rr < vrows && n < p.N) {
                 float4 o = *reinterpret_cast<const float4*>(patch + (4 * i + rsub) * TC_XLD + ch * 4);
-                if (p.res) {
-                  const int frr = rr / J, jr = rr - frr * J;
-                  const float4 r4 = ldg4(p.res + (map_frame(p.res_map, f0 + frr) * J + jr) * (long long)p.res_ld + n);
-                  o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-                }
+                if (p.res) { o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w; }
                 // rows of a tile are consecutive in the output: row index = f0*J + rr
                 *reinterpret_cast<float4*>(p.out + ((long long)f0 * J + rr) * p.ld_out + n) = o;
               }
@@ -904,7 +923,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           epi_bar_sync(ebar);
           // (a register/patch-staged, coalesced-store variant of this mix measured 70 % slower than the
           //  direct row-per-thread stores below: profiles/r01_tc_attribution.md)
-          if (valid && nb0 < p.N && GAST_EXP != 1) {
+          if (valid && nb0 < p.N) {
             const int nend = min(nb0 + 32, p.N);
             const int h_lo = nb0 / p.Cg, h_hi = (nend - 1) / p.Cg;
             for (int h = h_lo; h <= h_hi; ++h) {
@@ -934,7 +953,33 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
                   if (j < J) att[j] = att[j] * inv + __ldg(ck + j);
               }
               const int cbeg = max(h * p.Cg, nb0), cend = min((h + 1) * p.Cg, nend);
-              for (int n = cbeg; n < cend; n += 4) {
+              // y[i, n] = sum_j att[j] g[j, n]: 4 float4 columns per iteration = 16 independent FMA chains
+              // (one column at a time left the 17-deep chains latency-bound: 0.31 of 0.52 ms at C=128)
+              int n = cbeg;
+              for (; n + 16 <= cend; n += 16) {
+                float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0, o3 = o0;
+                const float* scol = Gs + fb * TC_XLD + (n - nb0);
+#pragma unroll
+                for (int j = 0; j < TC_JMAX; ++j) {
+                  if (j < J) {
+                    const float a_ = att[j];
+                    const float4 g0 = *reinterpret_cast<const float4*>(scol + j * TC_XLD);
+                    const float4 g1 = *reinterpret_cast<const float4*>(scol + j * TC_XLD + 4);
+                    const float4 g2 = *reinterpret_cast<const float4*>(scol + j * TC_XLD + 8);
+                    const float4 g3 = *reinterpret_cast<const float4*>(scol + j * TC_XLD + 12);
+                    o0.x = fmaf(a_, g0.x, o0.x); o0.y = fmaf(a_, g0.y, o0.y); o0.z = fmaf(a_, g0.z, o0.z); o0.w = fmaf(a_, g0.w, o0.w);
+                    o1.x = fmaf(a_, g1.x, o1.x); o1.y = fmaf(a_, g1.y, o1.y); o1.z = fmaf(a_, g1.z, o1.z); o1.w = fmaf(a_, g1.w, o1.w);
+                    o2.x = fmaf(a_, g2.x, o2.x); o2.y = fmaf(a_, g2.y, o2.y); o2.z = fmaf(a_, g2.z, o2.z); o2.w = fmaf(a_, g2.w, o2.w);
+                    o3.x = fmaf(a_, g3.x, o3.x); o3.y = fmaf(a_, g3.y, o3.y); o3.z = fmaf(a_, g3.z, o3.z); o3.w = fmaf(a_, g3.w, o3.w);
+                  }
+                }
+                float* op = p.out + orow * p.ld_out + n;
+                *reinterpret_cast<float4*>(op) = o0;
+                *reinterpret_cast<float4*>(op + 4) = o1;
+                *reinterpret_cast<float4*>(op + 8) = o2;
+                *reinterpret_cast<float4*>(op + 12) = o3;
+              }
+              for (; n < cend; n += 4) {
                 float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                 const float* scol = Gs + fb * TC_XLD + (n - nb0);
 #pragma unroll
@@ -945,7 +990,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
                     o.z = fmaf(att[j], g4.z, o.z); o.w = fmaf(att[j], g4.w, o.w);
                   }
                 }
-                if (GAST_EXP != 3 || o.x == 12345.678f) *reinterpret_cast<float4*>(p.out + orow * p.ld_out + n) = o;
+                *reinterpret_cast<float4*>(p.out + orow * p.ld_out + n) = o;
               }
             }
           }
@@ -1064,6 +1109,10 @@ inline int tc_prepare_weights(TcWeights& t, const float* W, int N, int K, cudaSt
 inline bool tc_supported(const GemmP& p, int epi, const TcWeights& t) {
   if (!t.ready || t.K != p.ldw) return false;
   if (p.J > TC_JMAX || p.N % 4) return false;
+  if (p.res) {   // the epilogue keeps residual row offsets as 32-bit counts of 16-byte units
+    const long long max_row = ((long long)(p.F / p.res_map.T_out) + 1) * p.res_map.T_in * p.J;
+    if (p.res_ld % 4 || max_row * p.res_ld * 4 >= (1LL << 34)) return false;
+  }
   for (int s = 0; s < p.nseg; ++s) {
     const ASeg& sg = p.seg[s];
     if (sg.K % TC_BK || sg.Kc % TC_BK || sg.ld % 4 || sg.tap_stride % 4) return false;

@@ -1,4 +1,5 @@
-"""Drop-in for the device-side subset of the reference's common/camera.py: `normalize_screen_coordinates`
+"""Device-side counterpart of a subset of the reference's common/camera.py (same names and signatures; under
+`device.` so that the reference module, which has more functions, is not shadowed): `normalize_screen_coordinates`
 (:8-12), `image_coordinates` (:15-19), `camera_to_world` (:27-28, one quaternion for all points as
 reconstruction.py:204 / gen_skes.py use it).  numpy in -> numpy out (through the device), CUDA tensor in ->
 CUDA tensor out."""

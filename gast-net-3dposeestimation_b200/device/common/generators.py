@@ -1,4 +1,6 @@
-"""Drop-in for the reference's common/generators.py with the batches assembled ON THE DEVICE.
+"""Device-side counterpart of the reference's common/generators.py: batches assembled ON THE DEVICE
+(import as device.common.generators: it yields CUDA tensors where the reference yields numpy arrays, so it
+does not shadow the reference module).
 
 `ChunkedGenerator` (generators.py:4-157) keeps the reference's constructor, pair list, shuffling
 (`np.random.RandomState(seed).permutation`, so the batch order is the reference's) and `next_epoch`

@@ -1,4 +1,5 @@
-"""Drop-in for the reference's common/loss.py: `mpjpe` (loss.py:5-11) and `p_mpjpe` (loss.py:14-53) on the
+"""Device-side counterpart of the reference's common/loss.py (same names and signatures; lives under
+`device.` so that it does not shadow the reference module, which has more functions): `mpjpe` (loss.py:5-11) and `p_mpjpe` (loss.py:14-53) on the
 device (gast_b200/pipeline.py, csrc/pipeline.cuh).  `mpjpe` is differentiable (forward and backward come
 from one kernel pass); `p_mpjpe` takes numpy arrays like the reference (main.py:281-283) or CUDA tensors."""
 import numpy as np

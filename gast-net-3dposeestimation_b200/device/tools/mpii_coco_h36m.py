@@ -1,4 +1,4 @@
-"""Drop-in for the reference's tools/mpii_coco_h36m.py: 2D keypoint format conversion on the device
+"""Device-side counterpart of the reference's tools/mpii_coco_h36m.py (import as device.tools.mpii_coco_h36m): 2D keypoint format conversion on the device
 (csrc/pipeline.cuh kpt_convert_kernel; float32 arithmetic in numpy's evaluation order, bit-identical for
 float32 input).  Same names and return values: (keypoints_h36m, valid_frames)."""
 import numpy as np

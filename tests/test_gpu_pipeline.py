@@ -1,5 +1,5 @@
 """GPU parity of the device-side caller steps (csrc/pipeline.cuh through the C ABI and
-the drop-in modules common/generators.py, common/loss.py, common/camera.py, tools/mpii_coco_h36m.py) against
+the same-name modules device/common/{generators,loss,camera}.py, device/tools/mpii_coco_h36m.py) against
 outputs of the unmodified reference (tests/golden/pipeline_17.npz) and the numpy oracle.
 Bars: bit-exact for index/byte work and the float32 keypoint arithmetic; 1e-6 relative for the float
 reductions (stated per test)."""
@@ -20,7 +20,7 @@ def G():
 
 
 def test_chunked_generator_on_device_bit_exact(G):
-    from common.generators import ChunkedGenerator
+    from device.common.generators import ChunkedGenerator
     lens, p2, p3, cams = dataset()
     gen = ChunkedGenerator(8, cams, p3, p2, 1, pad=13, causal_shift=0, shuffle=True, random_seed=1234, augment=True,
                            kps_left=LEFT, kps_right=RIGHT, joints_left=LEFT, joints_right=RIGHT)
@@ -62,7 +62,7 @@ def test_chunk_gather_large_vs_oracle():
 
 
 def test_unchunked_generator_on_device():
-    from common.generators import UnchunkedGenerator
+    from device.common.generators import UnchunkedGenerator
     t = load_golden('tta_17')
     gen = UnchunkedGenerator(None, None, [t['seq']], pad=13, causal_shift=0, augment=True, kps_left=LEFT, kps_right=RIGHT,
                              joints_left=LEFT, joints_right=RIGHT)
@@ -74,7 +74,7 @@ def test_unchunked_generator_on_device():
 
 
 def test_keypoint_formats_bit_exact(G):
-    import tools.mpii_coco_h36m as K
+    import device.tools.mpii_coco_h36m as K
     for fn, src, key in ((K.coco_h36m, 'k17', 'coco_h36m'), (K.mpii_h36m, 'k16', 'mpii_h36m'),
                          (K.coco_h36m_toe_format, 'k133', 'coco_toe')):
         out, valid = fn(G[src])                                   # numpy in -> numpy out, like the reference
@@ -94,7 +94,7 @@ def test_keypoint_formats_bit_exact(G):
 
 
 def test_camera_functions(G):
-    import common.camera as Cm
+    import device.common.camera as Cm
     assert np.array_equal(Cm.normalize_screen_coordinates(G['k17'], w=1920, h=1080), G['norm_screen'])
     assert np.allclose(Cm.image_coordinates(G['norm_screen'], w=1920, h=1080), G['img_coords'], rtol=0, atol=1e-4)
     got = Cm.camera_to_world(G['x3'], R=G['rot'], t=0)
@@ -104,7 +104,7 @@ def test_camera_functions(G):
 
 
 def test_mpjpe_forward_backward(G):
-    from common.loss import mpjpe
+    from device.common.loss import mpjpe
     pred = torch.from_numpy(G['mp_pred']).cuda().requires_grad_(True)
     tgt = torch.from_numpy(G['mp_tgt']).cuda()
     loss = mpjpe(pred, tgt)
@@ -125,7 +125,7 @@ def test_mpjpe_forward_backward(G):
 
 
 def test_p_mpjpe(G):
-    from common.loss import p_mpjpe
+    from device.common.loss import p_mpjpe
     from gast_b200 import pipeline as P
     per = P.p_mpjpe_per_frame(torch.from_numpy(G['pm_pred']).cuda(), torch.from_numpy(G['pm_tgt']).cuda()).cpu().numpy()
     assert np.abs(per - G['pm_per_frame']).max() < 2e-5            # the reference itself runs in float32
