@@ -760,8 +760,12 @@ extern "C" int gast_forward(gast_t* h, const float* x, float* y, int32_t B, int3
     if (c.filter_widths[0] * c.in_features > EXP_MAXKF) return fail("expand: filter_width*in_features > %d unsupported", EXP_MAXKF);
     long long thr = ((rows + EXP_ROWS - 1) / EXP_ROWS) * (C / 4);
     TimedLaunch tl(h, st, LK_EXPAND);
-    expand_kernel<<<cdiv(thr, 256), 256, 0, st>>>(x, h->We, h->be, mb.act[0], rows, J, T, g.T0, g.s0,
-                                                 c.filter_widths[0], c.in_features, C);
+    if (c.filter_widths[0] * c.in_features <= 6)
+      expand_kernel<6><<<cdiv(thr, 256), 256, 0, st>>>(x, h->We, h->be, mb.act[0], rows, J, T, g.T0, g.s0,
+                                                      c.filter_widths[0], c.in_features, C);
+    else
+      expand_kernel<EXP_MAXKF><<<cdiv(thr, 256), 256, 0, st>>>(x, h->We, h->be, mb.act[0], rows, J, T, g.T0, g.s0,
+                                                              c.filter_widths[0], c.in_features, C);
     h->launches++;
   }
   int cur = 0;

@@ -64,6 +64,7 @@ constexpr int TC_EN = 64;         // accumulator columns owned by one epilogue w
 constexpr int TC_STAGE_BYTES = 2 * 16384;            // B_hi, B_lo : 128 rows x 128 B each
 constexpr int TC_SLD = 68;                            // staging row stride (floats): conflict-free 16B rows
 constexpr int TC_MAX_NNZ = 64;    // SemCH coefficient slab rows
+constexpr int TC_MAXDEG = 6;      // SemCH: neighbours per joint kept in a packed register (17j: <= 5)
 constexpr int TC_JMAX = 20;
 constexpr int TC_XLD = 36;                            // raw A / 32-column staging row stride (floats): conflict-free row-per-thread access
 // Epilogue scratch, laid out per epilogue kind:
@@ -662,6 +663,21 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     long long tE_n = 0, tE_wait = 0, tE_tot = clock64(), tE_tiles = 0, tE_cw = 0, tE_cl = 0, tE_fl = 0;
     const uint32_t lane_off = ((uint32_t)(ew * 32) << 16) + (uint32_t)(eh * TC_EN);
     float* scratch = staging;                // TC_EPI_BYTES, laid out per epilogue kind below
+    // SemCH: neighbour list of this thread's joint for both masks: bits 0-7 first coefficient row,
+    // 8-11 degree (<= TC_MAXDEG, checked by tc_supported), then 5 bits per neighbour joint
+    unsigned long long nbr_pk0 = 0, nbr_pk1 = 0;
+    if (EPI == EPI_SEMCH) {
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        unsigned long long pk = 0;
+        if (p.coef[m]) {
+          const int z0 = p.nbr[m].row_ptr[ji], z1 = p.nbr[m].row_ptr[ji + 1];
+          pk = (unsigned long long)z0 | ((unsigned long long)(z1 - z0) << 8);
+          for (int z = z0; z < z1; ++z) pk |= (unsigned long long)p.nbr[m].col[z] << (12 + 5 * (z - z0));
+        }
+        if (m == 0) nbr_pk0 = pk; else nbr_pk1 = pk;
+      }
+    }
     for (int tile = cid; tile < total_tiles; tile += ncl) {
       const int tn = tile % n_tiles_n;
       const int f0 = tile_f0(tile);
@@ -678,20 +694,33 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         const int c0_ = (tn - mask_ * p.tiles_per_mask) * 64 + eh * 32;
         const int nnz_ = p.nbr[mask_].row_ptr[J];
         float* coef_w = scratch + 2 * 128 * TC_XLD + eh * 32;
-        for (int i = et; i < nnz_ * 8; i += 128) {
-          int z = i >> 3, g = (i & 7) * 4;
-          float4 cf = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (c0_ + g < p.C) cf = ldg4(p.coef[mask_] + (long long)z * p.C + c0_ + g);
-          *reinterpret_cast<float4*>(coef_w + z * TC_SLD + g) = cf;
+        // (all loads first, then the stores: nnz <= TC_MAX_NNZ = 64 rows x 8 float4 = at most 4 per thread;
+        //  load->store pairs one after the other exposed one global latency each, ~2000 cycles per tile)
+        float4 cfv[TC_MAX_NNZ * 8 / 128];
+#pragma unroll
+        for (int u = 0; u < TC_MAX_NNZ * 8 / 128; ++u) {
+          const int i = et + 128 * u, z = i >> 3, g = (i & 7) * 4;
+          cfv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < nnz_ * 8 && c0_ + g < p.C) cfv[u] = ldg4(p.coef[mask_] + (long long)z * p.C + c0_ + g);
+        }
+#pragma unroll
+        for (int u = 0; u < TC_MAX_NNZ * 8 / 128; ++u) {
+          const int i = et + 128 * u, z = i >> 3, g = (i & 7) * 4;
+          if (i < nnz_ * 8) *reinterpret_cast<float4*>(coef_w + z * TC_SLD + g) = cfv[u];
         }
       }
       float* ab_g = eh ? (scratch + 2 * 128 * TC_XLD) : ab_s;   // per-group copy of the a/b tile
       if (EPI == EPI_GLOBAL) {
-        const int H2_ = 2 * p.heads;
-        for (int i = et; i < 128 * H2_; i += 128) {
-          int rr = i / H2_;
-          ab_g[i] = (rr < vrows) ? __ldg(p.ab + ((long long)f0 * J) * H2_ + i) : 0.f;
+        const int H2_ = 2 * p.heads;                  // <= 8 (tc_supported): loads first, then the stores
+        float abv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = et + 128 * u;
+          abv[u] = (u < H2_ && i / H2_ < vrows) ? __ldg(p.ab + ((long long)f0 * J) * H2_ + i) : 0.f;
         }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (u < H2_) ab_g[et + 128 * u] = abv[u];
       }
 
       // ---- level-2 accumulation: group sums (TMEM) -> fp32 registers, round-to-nearest adds.
@@ -844,7 +873,6 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         // channels c0 .. c0+31.
         const int mask = tn / p.tiles_per_mask;
         const int c0 = (tn - mask * p.tiles_per_mask) * 64 + eh * 32;
-        const NbrTable& nb = p.nbr[mask];
         float* Hs = scratch + eh * (128 * TC_XLD);               // [128 rows][32 ch], stride TC_XLD
         const float* coef_r = scratch + 2 * 128 * TC_XLD + eh * 32;
 #pragma unroll
@@ -855,7 +883,11 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         epi_bar_sync(ebar);
         float ov[32];
         {
-          const int z0 = valid ? nb.row_ptr[ji] : 0, z1 = valid ? nb.row_ptr[ji + 1] : 0;
+          // this row's neighbour list comes packed in a register (built once per kernel): the loop is
+          // fully unrolled and predicated, so the shared-memory loads of all neighbours can be in flight
+          // together (a runtime z loop with an indexed constant load per step exposed ~2 latencies per neighbour)
+          const unsigned long long pk = mask ? nbr_pk1 : nbr_pk0;
+          const int z0 = (int)(pk & 0xff), cnt = valid ? (int)((pk >> 8) & 0xf) : 0;
 #pragma unroll
           for (int gq = 0; gq < 2; ++gq) {           // 16 channels at a time
             float o[16];
@@ -866,18 +898,21 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
               if (p.shift && c < p.C) sh = ldg4(p.shift + mask * p.C + c);
               o[g * 4] = sh.x; o[g * 4 + 1] = sh.y; o[g * 4 + 2] = sh.z; o[g * 4 + 3] = sh.w;
             }
-            for (int z = z0; z < z1; ++z) {
-              const int jn = nb.col[z];
-              const float* hrow = Hs + (fb + jn) * TC_XLD + gq * 16;
-              const float* crow = coef_r + z * TC_SLD + gq * 16;
-              const bool self = (jn == ji);
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float4 cf = *reinterpret_cast<const float4*>(crow + g * 4);
-                float4 hv = *reinterpret_cast<const float4*>(hrow + g * 4);
-                if (self) hv = make_float4(h0[gq * 16 + g * 4], h0[gq * 16 + g * 4 + 1], h0[gq * 16 + g * 4 + 2], h0[gq * 16 + g * 4 + 3]);
-                o[g * 4] = fmaf(cf.x, hv.x, o[g * 4]); o[g * 4 + 1] = fmaf(cf.y, hv.y, o[g * 4 + 1]);
-                o[g * 4 + 2] = fmaf(cf.z, hv.z, o[g * 4 + 2]); o[g * 4 + 3] = fmaf(cf.w, hv.w, o[g * 4 + 3]);
+            for (int k = 0; k < TC_MAXDEG; ++k) {
+              if (k < cnt) {
+                const int jn = (int)((pk >> (12 + 5 * k)) & 31);
+                const float* hrow = Hs + (fb + jn) * TC_XLD + gq * 16;
+                const float* crow = coef_r + (z0 + k) * TC_SLD + gq * 16;
+                const bool self = (jn == ji);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  float4 cf = *reinterpret_cast<const float4*>(crow + g * 4);
+                  float4 hv = *reinterpret_cast<const float4*>(hrow + g * 4);
+                  if (self) hv = make_float4(h0[gq * 16 + g * 4], h0[gq * 16 + g * 4 + 1], h0[gq * 16 + g * 4 + 2], h0[gq * 16 + g * 4 + 3]);
+                  o[g * 4] = fmaf(cf.x, hv.x, o[g * 4]); o[g * 4 + 1] = fmaf(cf.y, hv.y, o[g * 4 + 1]);
+                  o[g * 4 + 2] = fmaf(cf.z, hv.z, o[g * 4 + 2]); o[g * 4 + 3] = fmaf(cf.w, hv.w, o[g * 4 + 3]);
+                }
               }
             }
 #pragma unroll
@@ -894,7 +929,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           // coalesced: 8 lanes cover the 128-byte row segment of one row, 4 rows per instruction
           const int rs = lane >> 3, chq = lane & 7;
           const int c = c0 + chq * 4;
-#pragma unroll 4
+#pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = ew * 32 + 4 * i + rs;
             if (rr < vrows && c < p.C)
@@ -954,7 +989,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
               }
               const int cbeg = max(h * p.Cg, nb0), cend = min((h + 1) * p.Cg, nend);
               // y[i, n] = sum_j att[j] g[j, n]: 4 float4 columns per iteration = 16 independent FMA chains
-              // (one column at a time left the 17-deep chains latency-bound: 0.31 of 0.52 ms at C=128)
+              // (measured neutral against one float4 at a time; an explicit one-step-ahead load of g was 4 % slower)
               int n = cbeg;
               for (; n + 16 <= cend; n += 16) {
                 float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0, o3 = o0;
@@ -1120,8 +1155,12 @@ inline bool tc_supported(const GemmP& p, int epi, const TcWeights& t) {
   }
   if (epi == EPI_SEMCH) {
     if (p.C % 4) return false;
-    for (int m = 0; m < 2; ++m)
-      if (p.coef[m] && p.nbr[m].row_ptr[p.J] > TC_MAX_NNZ) return false;
+    for (int m = 0; m < 2; ++m) {
+      if (!p.coef[m]) continue;
+      if (p.nbr[m].row_ptr[p.J] > TC_MAX_NNZ) return false;
+      for (int j = 0; j < p.J; ++j)
+        if (p.nbr[m].row_ptr[j + 1] - p.nbr[m].row_ptr[j] > TC_MAXDEG) return false;
+    }
   }
   if (epi == EPI_GLOBAL && (p.Cg % 4 || p.heads > 4)) return false;
   return true;

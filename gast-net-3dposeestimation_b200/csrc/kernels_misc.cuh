@@ -15,6 +15,7 @@ namespace gast {
 // load instructions per output float4 (first version: 0.50 ms for 321 MB, 10x off the HBM bound).
 constexpr int EXP_ROWS = 8;
 constexpr int EXP_MAXKF = 10;   // taps * in_features supported by the register path (3*2 = 6; 5*2 = 10)
+template <int KFT>   // register-resident K = taps * in_features rounded up: 6 (3 taps x 2) or EXP_MAXKF
 __global__ void expand_kernel(const float* __restrict__ x, const float* __restrict__ We,
                               const float* __restrict__ be, float* __restrict__ out,
                               long long rows, int J, int T, int T0, int stride, int taps,
@@ -26,35 +27,47 @@ __global__ void expand_kernel(const float* __restrict__ x, const float* __restri
   const long long grp = idx / cq;
   const int c = (int)(idx - grp * cq) * 4;
   const int KF = taps * Fin;
-  float w[4][EXP_MAXKF];
+  float w[4][KFT];
 #pragma unroll
   for (int q = 0; q < 4; ++q)
 #pragma unroll
-    for (int k = 0; k < EXP_MAXKF; ++k) w[q][k] = (k < KF) ? __ldg(We + (c + q) * KF + k) : 0.f;
+    for (int k = 0; k < KFT; ++k) w[q][k] = (k < KF) ? __ldg(We + (c + q) * KF + k) : 0.f;
   const float4 b4 = ldg4(be + c);
   const long long r0 = grp * EXP_ROWS;
+  // All EXP_ROWS x KF input values are requested before the first FMA (rows past the end re-read the
+  // last row): with the loads issued row by row the kernel ran at 1/3 of its output-stream bound.
+  float xv[EXP_ROWS][KFT];
 #pragma unroll
   for (int rr = 0; rr < EXP_ROWS; ++rr) {
-    const long long row = r0 + rr;
-    if (row >= rows) break;
+    const long long row = min(r0 + rr, rows - 1);
     // 32-bit index math (the host checks rows < 2^31): 64-bit divisions cost ~100 instructions each
     const int f = (int)row / J;
     const int j = (int)row - f * J;
     const int b = f / T0;
     const int t = f - b * T0;
     const float* xin = x + (((long long)b * T + (long long)t * stride) * J + j) * Fin;
-    float v0 = b4.x, v1 = b4.y, v2 = b4.z, v3 = b4.w;
 #pragma unroll
-    for (int k = 0; k < EXP_MAXKF; ++k) {
+    for (int k = 0; k < KFT; ++k) {
       if (k < KF) {
         const int kk = k / Fin, i = k - kk * Fin;
-        const float xv = __ldg(xin + (long long)kk * J * Fin + i);
-        v0 = fmaf(w[0][k], xv, v0); v1 = fmaf(w[1][k], xv, v1);
-        v2 = fmaf(w[2][k], xv, v2); v3 = fmaf(w[3][k], xv, v3);
+        xv[rr][k] = __ldg(xin + (long long)kk * J * Fin + i);
+      } else {
+        xv[rr][k] = 0.f;
       }
     }
-    *reinterpret_cast<float4*>(out + row * C + c) =
-        make_float4(fmaxf(v0, 0.f), fmaxf(v1, 0.f), fmaxf(v2, 0.f), fmaxf(v3, 0.f));
+  }
+#pragma unroll
+  for (int rr = 0; rr < EXP_ROWS; ++rr) {
+    const long long row = r0 + rr;
+    float v0 = b4.x, v1 = b4.y, v2 = b4.z, v3 = b4.w;
+#pragma unroll
+    for (int k = 0; k < KFT; ++k) {
+      v0 = fmaf(w[0][k], xv[rr][k], v0); v1 = fmaf(w[1][k], xv[rr][k], v1);
+      v2 = fmaf(w[2][k], xv[rr][k], v2); v3 = fmaf(w[3][k], xv[rr][k], v3);
+    }
+    if (row < rows)
+      *reinterpret_cast<float4*>(out + row * C + c) =
+          make_float4(fmaxf(v0, 0.f), fmaxf(v1, 0.f), fmaxf(v2, 0.f), fmaxf(v3, 0.f));
   }
 }
 

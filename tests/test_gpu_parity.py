@@ -252,3 +252,21 @@ def test_tta_on_device_matches_reference_generator():
     out = tta.evaluate_sequence(m, clip, left, right, left, right)
     assert out.shape == (277, 17, 3)
     assert np.abs(out.cpu().numpy() - O.tta_merge(g['y'], left, right)).max() < TOL
+
+
+def test_pipelined_lifter_matches_direct_calls():
+    """Host-fed streaming API (gast_b200/stream.py): same poses as one direct call per batch, in order, with the
+    uploads / downloads on a copy stream."""
+    from gast_b200.stream import PipelinedLifter
+    g = load_golden('cfg2_17_333_c128_full_T27')
+    m = build_model(g['meta'])
+    xs = [torch.from_numpy(synth.synth_input(64, 27, 17, 2, seed=100 + i)).pin_memory() for i in range(5)]
+    outs = [torch.empty((64, 1, 17, 3), dtype=torch.float32).pin_memory() for _ in range(5)]
+    PipelinedLifter(m, depth=2).run(xs, outs)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        for x, o in zip(xs, outs):
+            ref = m(x.cuda()).cpu()
+            assert torch.equal(ref, o)
+    with pytest.raises(RuntimeError):
+        PipelinedLifter(build_model(g['meta'], device='cpu'))
