@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <unordered_map>
@@ -98,7 +99,7 @@ struct gast_handle {
 };
 
 enum { LK_EXPAND = 0, LK_GEMM_PLAIN = 1, LK_GEMM_SEMCH = 2, LK_GEMM_GLOBAL = 3, LK_ROWDOT = 4, LK_SHRINK = 5,
-       LK_TC_PLAIN = 6, LK_TC_SEMCH = 7, LK_TC_GLOBAL = 8 };
+       LK_TC_PLAIN = 6, LK_TC_SEMCH = 7, LK_TC_GLOBAL = 8, LK_GLOBAL_MIX = 9 };
 
 struct TimedLaunch {   // RAII: event pair around one launch when timing is on
   gast_handle* h; cudaStream_t st; bool on;
@@ -643,6 +644,31 @@ static int run_global(gast_handle* h, cudaStream_t st, BlockConsts& b, const flo
   const int C = b.C, J = h->cfg.num_joints, Ng = b.heads * b.Cg;
   if (launch_rowdot(h, st, X, C, b, w.AB, F * J)) return 1;
   GemmP p;
+  // tcgen05 core, block / MultiGlobalGraph: plain `g` GEMM (flat 128-row tiles) into out_G as scratch, then the
+  // attention mix as its own full-occupancy kernel into Y.  Measured faster than the mix fused into the GEMM
+  // epilogue (the fused form stays for the FFMA core and the single-head kind, and as GAST_GLOBAL_FUSED=1).
+  static const bool fused_env = getenv("GAST_GLOBAL_FUSED") && atoi(getenv("GAST_GLOBAL_FUSED")) != 0;
+  if (!fused_env && h->gemm_core == 0 && kind != GAST_KIND_GLOBAL_HEAD && b.tc_g.ready && Ng % 4 == 0 &&
+      b.Cg % 4 == 0 && J <= MIX_JMAX) {
+    gemm_defaults_flat(p, h, F);
+    p.nseg = 1; p.seg[0] = seg_flat(X, C, C);
+    p.W = b.Wg; p.ldw = C; p.N = Ng; p.out = out_G; p.ld_out = Ng; p.bias = b.bg; p.relu = 0;
+    if (launch_gemm(h, st, EPI_PLAIN, p, &b.tc_g)) return 1;
+    const int G4 = Ng / 4;
+    int fpb = G4 >= MIX_THREADS ? 1 : MIX_THREADS / G4;
+    fpb = std::max(1, std::min(fpb, (int)(40 * 1024 / (sizeof(float) * b.heads * J * MIX_JP))));   // attention rows fit 40 KB
+    const size_t smem = sizeof(float) * (size_t)fpb * b.heads * J * MIX_JP;
+    {
+      TimedLaunch tl(h, st, LK_GLOBAL_MIX);
+      global_mix_kernel<<<cdiv(F, fpb), MIX_THREADS, smem, st>>>(out_G, Ng, w.AB, b.Ck, w.Y, Ng, F, J, b.heads, b.Cg, fpb);
+      h->launches++;
+    }
+    CUDA_OK(cudaGetLastError());
+    gemm_defaults_flat(p, h, F);
+    p.nseg = 1; p.seg[0] = seg_flat(w.Y, C, C);
+    p.W = b.Wgc; p.ldw = C; p.N = C; p.out = out_G; p.ld_out = C; p.bias = b.bgc; p.relu = 1;
+    return launch_gemm(h, st, EPI_PLAIN, p, &b.tc_gc);
+  }
   gemm_defaults(p, h, F);
   p.nseg = 1; p.seg[0] = seg_flat(X, C, C);
   p.W = b.Wg; p.ldw = C; p.N = Ng;

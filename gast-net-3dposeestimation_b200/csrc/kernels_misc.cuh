@@ -211,6 +211,92 @@ __global__ void tta_merge_kernel(const float* __restrict__ pred, float* __restri
 // ---------------------------------------------------------------------------------------
 // parameter preparation (eval mode)
 // ---------------------------------------------------------------------------------------
+// Attention mix of MultiGlobalGraph as its own kernel (global_attention.py:74-80):
+//   Y[f, i, c] = sum_j att_h(c)[f, i, j] . G[f, j, c],   att_h = softmax_j(LeakyReLU_0.2(a_i + b_j)) + C_k
+// Same arithmetic as the fused epilogue of the `g` GEMM, but at full occupancy: inside the GEMM only
+// 8 warps per SM can work on it and the mix is latency-bound there (ncu: tensor pipe 11 % busy, the
+// epilogue warps 97 % busy, profiles/r01_v19_lines_global.txt).  One thread = (frame, 4 channels): the 17
+// float4 of its channel group are read once (coalesced along the channel axis) and kept in registers, the
+// attention rows of the block's frames are computed once into shared memory.
+// ---------------------------------------------------------------------------------------
+constexpr int MIX_THREADS = 128;
+constexpr int MIX_JMAX = 20;
+constexpr int MIX_JP = 20;        // padded row length of an attention row in shared memory (float4 reads)
+
+__global__ void __launch_bounds__(MIX_THREADS)
+global_mix_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ ab, const float* __restrict__ ck,
+                  float* __restrict__ Y, int ldy, long long F, int J, int heads, int Cg, int fpb) {
+  extern __shared__ __align__(16) float att_s[];            // [fpb][heads][J][MIX_JP]
+  const int tid = threadIdx.x;
+  const int H2 = 2 * heads;
+  const long long f0 = (long long)blockIdx.x * fpb;
+  // ---- attention rows of this block's frames
+  const int nrow = fpb * heads * J;
+  for (int e = tid; e < nrow; e += MIX_THREADS) {
+    const int i = e % J, h = (e / J) % heads, fs = e / (J * heads);
+    const long long f = f0 + fs;
+    float* dst = att_s + (size_t)e * MIX_JP;
+    if (f < F) {
+      const float* abf = ab + (f * J) * H2;
+      const float a = __ldg(abf + i * H2 + 2 * h);
+      float v[MIX_JMAX];
+      float mx = -3.4e38f;
+#pragma unroll
+      for (int j = 0; j < MIX_JMAX; ++j)
+        if (j < J) {
+          float s = a + __ldg(abf + j * H2 + 2 * h + 1);
+          s = (s >= 0.f) ? s : 0.2f * s;
+          v[j] = s;
+          mx = fmaxf(mx, s);
+        }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < MIX_JMAX; ++j)
+        if (j < J) { v[j] = expf(v[j] - mx); sum += v[j]; }
+      const float inv = 1.f / sum;
+      const float* ckr = ck + ((long long)h * J + i) * J;
+#pragma unroll
+      for (int j = 0; j < MIX_JMAX; ++j) dst[j] = (j < J) ? v[j] * inv + __ldg(ckr + j) : 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < MIX_JMAX; ++j) dst[j] = 0.f;
+    }
+  }
+  __syncthreads();
+  // ---- mix: thread = (frame slot, group of 4 channels)
+  const int G4 = (heads * Cg) >> 2;
+  for (int w = tid; w < fpb * G4; w += MIX_THREADS) {
+    const int fs = w / G4, c = (w - fs * G4) * 4;
+    const long long f = f0 + fs;
+    if (f >= F) continue;
+    const int h = c / Cg;
+    float4 g[MIX_JMAX];
+    const float* gp = G + (f * J) * (long long)ldg + c;
+#pragma unroll
+    for (int j = 0; j < MIX_JMAX; ++j)
+      if (j < J) g[j] = ldg4(gp + (long long)j * ldg);
+    const float* arow = att_s + (size_t)((fs * heads + h) * J) * MIX_JP;
+    float* yp = Y + (f * J) * (long long)ldy + c;
+    for (int i = 0; i < J; ++i) {
+      float a[MIX_JMAX];
+#pragma unroll
+      for (int q = 0; q < MIX_JMAX / 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(arow + i * MIX_JP + q * 4);
+        a[q * 4] = t.x; a[q * 4 + 1] = t.y; a[q * 4 + 2] = t.z; a[q * 4 + 3] = t.w;
+      }
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < MIX_JMAX; ++j)
+        if (j < J) {
+          o.x = fmaf(a[j], g[j].x, o.x); o.y = fmaf(a[j], g[j].y, o.y);
+          o.z = fmaf(a[j], g[j].z, o.z); o.w = fmaf(a[j], g[j].w, o.w);
+        }
+      *reinterpret_cast<float4*>(yp + (long long)i * ldy) = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 struct BnP {  // eval BatchNorm as y = x*scale + shift ; null weight => identity
   const float* w; const float* b; const float* rm; const float* rv;
 };

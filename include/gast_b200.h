@@ -109,7 +109,7 @@ int32_t gast_last_tc_launch_count(const gast_t* h);
  * kernel launch with a CUDA event pair on the caller's stream; gast_get_timings waits for
  * them and returns up to max_n (milliseconds, kind) pairs of the last forward.  kinds:
  * 0 expand, 1-3 FFMA GEMM (plain/SemCH/global epilogue), 4 theta/phi row-dot, 5 shrink,
- * 6-8 tcgen05 GEMM (plain/SemCH/global). */
+ * 6-8 tcgen05 GEMM (plain/SemCH/global), 9 attention mix of MultiGlobalGraph as its own kernel. */
 int gast_set_timing(gast_t* h, int32_t on);
 int32_t gast_get_timings(gast_t* h, int32_t max_n, float* ms, int32_t* kinds);
 
