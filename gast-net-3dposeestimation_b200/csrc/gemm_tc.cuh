@@ -60,6 +60,13 @@ constexpr int TC_THREADS = 512;   // 4 warpgroups: A converters | epilogue (cols
 #endif
 constexpr int TC_REG_A = GAST_TC_REG_A, TC_REG_E = GAST_TC_REG_E, TC_REG_M = GAST_TC_REG_M;
 static_assert(TC_REG_A + 2 * TC_REG_E + TC_REG_M <= 512, "register file over-subscribed");
+// k-step after which the MMA warp probes the barriers of the NEXT chunk: 3 = after the last MMA of the chunk
+// (the operands are surely there by then, and the probes overlap the MMAs still queued in the tensor pipe);
+// 1 = early (the probes often failed and a blocking wait followed at the top of the next chunk)
+#ifndef GAST_TC_PROBE_K
+#define GAST_TC_PROBE_K 3
+#endif
+constexpr int TC_PROBE_K = GAST_TC_PROBE_K;
 constexpr int TC_EN = 64;         // accumulator columns owned by one epilogue warpgroup
 constexpr int TC_STAGE_BYTES = 2 * 16384;            // B_hi, B_lo : 128 rows x 128 B each
 constexpr int TC_SLD = 68;                            // staging row stride (floats): conflict-free 16B rows
@@ -583,7 +590,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       // their execution time), so anything else the thread does leaves the pipe idle.  The
       // readiness probes of the NEXT chunk (~70 cycles each) are therefore launched between the
       // MMAs of the current one and only consumed at the top of the next iteration.
-      bool pre_a = false, pre_b = false;
+      bool pre_a = false, pre_b = false, pre_m = false;
       for (int tile = cid; tile < total_tiles; tile += ncl) {
         mbar_wait(bar0 + BC_EMPTY, tphase ^ 1);  // corr buffer drained by the epilogue of the previous tile
         const uint32_t d_corr = tmem_base + CORR_COL;
@@ -592,7 +599,8 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           const int cg = c % TC_FLUSH;                    // position in the flush group
           long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
           if (DBG == 6) t0 = clock64();
-          if (cg == 0) mbar_wait(bar0 + BM_EMPTY + 8 * mb, ((mcount / NMAIN) & 1) ^ 1);
+          if (cg == 0 && !pre_m) mbar_wait(bar0 + BM_EMPTY + 8 * mb, ((mcount / NMAIN) & 1) ^ 1);
+          pre_m = false;
           if (DBG == 6) t1 = clock64();
           if (!pre_a) mbar_wait(bar0 + BA_FULL + 8 * as, aphase);
           if (DBG == 6) t2 = clock64();
@@ -625,10 +633,14 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
               }
             }
             __syncwarp();
-            if (k == 1) pre_a = mbar_try(bar0 + BA_FULL + 8 * as_n, aph_n);
-            if (k == 2) pre_b = mbar_try(bar0 + BB_FULL + 8 * bs_n, bph_n);
+            if (k == TC_PROBE_K) pre_a = mbar_try(bar0 + BA_FULL + 8 * as_n, aph_n);
+            if (k == TC_PROBE_K + (TC_PROBE_K < 3 ? 1 : 0)) pre_b = mbar_try(bar0 + BB_FULL + 8 * bs_n, bph_n);
           }
-          if (last_of_group) ++mcount;
+          if (last_of_group) {
+            ++mcount;
+            // the next chunk opens a flush group: probe its accumulator buffer as well
+            if (TC_PROBE_K >= 3) pre_m = mbar_try(bar0 + BM_EMPTY + 8 * (mcount % NMAIN), ((mcount / NMAIN) & 1) ^ 1);
+          }
           bs = bs_n; bphase = bph_n;
           as = as_n; aphase = aph_n;
           if (DBG == 6) {

@@ -27,24 +27,28 @@ __global__ void expand_kernel(const float* __restrict__ x, const float* __restri
   const long long grp = idx / cq;
   const int c = (int)(idx - grp * cq) * 4;
   const int KF = taps * Fin;
+  // folded weights are stored [k][C]: one coalesced float4 (4 channels) per k (the [C][k] layout made every lane
+  // of 24 scalar loads hit a different sector; measured 0.309 -> 0.286 ms)
   float w[4][KFT];
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
-#pragma unroll
-    for (int k = 0; k < KFT; ++k) w[q][k] = (k < KF) ? __ldg(We + (c + q) * KF + k) : 0.f;
+  for (int k = 0; k < KFT; ++k) {
+    float4 wk = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < KF) wk = ldg4(We + (long long)k * C + c);
+    w[0][k] = wk.x; w[1][k] = wk.y; w[2][k] = wk.z; w[3][k] = wk.w;
+  }
   const float4 b4 = ldg4(be + c);
   const long long r0 = grp * EXP_ROWS;
   // All EXP_ROWS x KF input values are requested before the first FMA (rows past the end re-read the
   // last row): with the loads issued row by row the kernel ran at 1/3 of its output-stream bound.
   float xv[EXP_ROWS][KFT];
+  // (clip, frame, joint) of the first row by division (32-bit: the host checks rows < 2^31), the following rows by
+  // increment: the 16 integer divisions per thread of the first version were a third of its instructions
+  int f = (int)r0 / J;
+  int j = (int)r0 - f * J;
+  int b = f / T0;
+  int t = f - b * T0;
 #pragma unroll
   for (int rr = 0; rr < EXP_ROWS; ++rr) {
-    const long long row = min(r0 + rr, rows - 1);
-    // 32-bit index math (the host checks rows < 2^31): 64-bit divisions cost ~100 instructions each
-    const int f = (int)row / J;
-    const int j = (int)row - f * J;
-    const int b = f / T0;
-    const int t = f - b * T0;
     const float* xin = x + (((long long)b * T + (long long)t * stride) * J + j) * Fin;
 #pragma unroll
     for (int k = 0; k < KFT; ++k) {
@@ -54,6 +58,9 @@ __global__ void expand_kernel(const float* __restrict__ x, const float* __restri
       } else {
         xv[rr][k] = 0.f;
       }
+    }
+    if (r0 + rr + 1 < rows) {                 // rows past the end re-read the last row
+      if (++j == J) { j = 0; if (++t == T0) { t = 0; ++b; } }
     }
   }
 #pragma unroll
@@ -116,39 +123,50 @@ __global__ void rowdot8_kernel(const float* __restrict__ X, int ldx, const float
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int sel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);   // q owned after the butterfly
   const float cq = __ldg(cab + sel);
-  for (long long row = warp; row < rows; row += nwarps) {
-    const float* xr = X + row * ldx;
-    float v[8];
+  // two rows per iteration: both rows' loads are in flight before the first FMA (one 512-byte request per
+  // warp at a time left the kernel at 2.2 TB/s)
+  for (long long row0 = warp; row0 < rows; row0 += 2 * nwarps) {
+    const long long row1 = row0 + nwarps;
+    const bool has1 = row1 < rows;
+    const float* xr0 = X + row0 * ldx;
+    const float* xr1 = X + (has1 ? row1 : row0) * ldx;
+    float va[8], vb[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = 0.f;
+    for (int q = 0; q < 8; ++q) { va[q] = 0.f; vb[q] = 0.f; }
     for (int k = lane * 4; k < K; k += 128) {
-      const float4 xv = ldg4(xr + k);
+      const float4 xa = ldg4(xr0 + k);
+      const float4 xb = ldg4(xr1 + k);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 u = *reinterpret_cast<const float4*>(us + q * K + k);
-        v[q] = fmaf(xv.x, u.x, fmaf(xv.y, u.y, fmaf(xv.z, u.z, fmaf(xv.w, u.w, v[q]))));
+        va[q] = fmaf(xa.x, u.x, fmaf(xa.y, u.y, fmaf(xa.z, u.z, fmaf(xa.w, u.w, va[q]))));
+        vb[q] = fmaf(xb.x, u.x, fmaf(xb.y, u.y, fmaf(xb.z, u.z, fmaf(xb.w, u.w, vb[q]))));
       }
     }
-    // halving butterfly: after the xor-16 step a lane keeps 4 of the 8 sums, then 2, then 1
-    float w4[4], w2[2], w1;
     const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float keep = hi16 ? v[i + 4] : v[i], send = hi16 ? v[i] : v[i + 4];
-      w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
+    for (int r = 0; r < 2; ++r) {
+      const float* v = r ? vb : va;
+      // halving butterfly: after the xor-16 step a lane keeps 4 of the 8 sums, then 2, then 1
+      float w4[4], w2[2], w1;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const float keep = hi8 ? w4[i + 2] : w4[i], send = hi8 ? w4[i] : w4[i + 2];
-      w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      for (int i = 0; i < 4; ++i) {
+        const float keep = hi16 ? v[i + 4] : v[i], send = hi16 ? v[i] : v[i + 4];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float keep = hi8 ? w4[i + 2] : w4[i], send = hi8 ? w4[i] : w4[i + 2];
+        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      {
+        const float keep = hi4 ? w2[1] : w2[0], send = hi4 ? w2[0] : w2[1];
+        w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+      w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+      if ((lane & 3) == 0 && (r == 0 || has1)) ab[(r ? row1 : row0) * 8 + sel] = w1 + cq;
     }
-    {
-      const float keep = hi4 ? w2[1] : w2[0], send = hi4 ? w2[0] : w2[1];
-      w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
-    w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
-    if ((lane & 3) == 0) ab[row * 8 + sel] = w1 + cq;
   }
 }
 
@@ -377,7 +395,7 @@ __global__ void global_collapse_kernel(float* __restrict__ U, float* __restrict_
   }
 }
 
-// We[c][kk*Fin+i] = w[c][i][kk] * s_in[i] * s_e[c];  be[c] = s_e[c]*sum w*t_in + t_e[c]
+// We[kk*Fin+i][c] = w[c][i][kk] * s_in[i] * s_e[c];  be[c] = s_e[c]*sum w*t_in + t_e[c]
 __global__ void expand_fold_kernel(float* __restrict__ We, float* __restrict__ be,
                                    const float* __restrict__ w, int C, int Fin, int taps,
                                    BnP bin, BnP bex) {
@@ -391,7 +409,7 @@ __global__ void expand_fold_kernel(float* __restrict__ We, float* __restrict__ b
       float si = bin.w[i] / sqrtf(bin.rv[i] + BN_EPS);
       float ti = bin.b[i] - bin.rm[i] * si;
       float wv = w[((long long)c * Fin + i) * taps + kk];
-      We[(long long)c * taps * Fin + kk * Fin + i] = wv * si * se;
+      We[(long long)(kk * Fin + i) * C + c] = wv * si * se;   // [k][C]: the expand kernel reads a float4 of 4 channels per k
       acc = fmaf(wv, ti, acc);
     }
   be[c] = se * acc + te;
