@@ -9,7 +9,8 @@ rows = list(csv.reader(open(path)))
 start = [i for i, r in enumerate(rows) if len(r) >= 2 and r[0] == 'File Path' and r[1].endswith(fname)][0]
 h = rows[start + 2]
 iS, iI = h.index('# Samples'), h.index('Instructions Executed')
-iW, iWi = h.index('L1 Wavefronts Shared'), h.index('L1 Wavefronts Shared Ideal')
+iW = h.index('L1 Wavefronts Shared') if 'L1 Wavefronts Shared' in h else 10 ** 6
+iWi = h.index('L1 Wavefronts Shared Ideal') if 'L1 Wavefronts Shared Ideal' in h else 10 ** 6
 stall = [i for i, c in enumerate(h) if c.startswith('stall_') and 'Not Issued' not in c]
 cur, src, agg = None, {}, {}
 for r in rows[start + 3:]:

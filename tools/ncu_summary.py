@@ -32,12 +32,20 @@ def val(r, name):
     return v
 
 
-print('| # | epilogue | ' + ' | '.join(x[1] for x in cols) + ' |')
+print('| # | kernel | ' + ' | '.join(x[1] for x in cols) + ' |')
 print('|---|---|' + '---|' * len(cols))
 tot_r = tot_w = tot_t = 0.0
+fam_r = fam_w = 0.0
+fam_n = 0
 for i, r in enumerate(data):
     kn = r[c('Kernel Name')]
-    epi = EPI.get(kn[kn.index('<') + 1:].replace('(int)', '').strip()[0], '?') if '<' in kn else '?'
+    if 'gemm_tc_kernel' in kn:
+        epi = 'gemm ' + EPI.get(kn[kn.index('<') + 1:].replace('(int)', '').strip()[0], '?')
+    else:
+        epi = next((n for n in ('expand', 'rowdot', 'global_mix', 'shrink') if n in kn), kn[:16])
+    fam = epi.startswith('gemm') or epi == 'global_mix'
+    if fam:
+        fam_r += val(r, 'dram__bytes_read.sum'); fam_w += val(r, 'dram__bytes_write.sum'); fam_n += 1
     vals = [val(r, x[0]) for x in cols]
     tot_t += val(r, 'gpu__time_duration.sum')
     tot_r += val(r, 'dram__bytes_read.sum')
@@ -45,4 +53,6 @@ for i, r in enumerate(data):
     print('| %d | %s | ' % (i, epi) + ' | '.join(('%.0f' % v) if v >= 100 else ('%.1f' % v) for v in vals) + ' |')
 print()
 print(json.dumps({'launches': len(data), 'sum_duration_us': tot_t, 'dram_read_MB': tot_r, 'dram_write_MB': tot_w,
-                  'dram_bytes_per_step': (tot_r + tot_w) * 1e6, 'per_launch_mean_bytes': (tot_r + tot_w) * 1e6 / max(len(data), 1)}))
+                  'dram_bytes_per_step_all_kernels': (tot_r + tot_w) * 1e6,
+                  'gemm_family_launches': fam_n, 'dram_bytes_per_step': (fam_r + fam_w) * 1e6,
+                  'per_launch_mean': (fam_r + fam_w) * 1e6 / max(fam_n, 1)}))
