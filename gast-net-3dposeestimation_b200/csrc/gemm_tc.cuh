@@ -44,13 +44,13 @@ struct TcWeights {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;
 constexpr int TC_BSTAGES = 3;   // B (weights) ring in shared memory, filled by TMA
-constexpr int TC_RSTAGES = 4;   // raw A ring in shared memory, filled by cp.async (no register staging, no MSHR cap)
-constexpr int TC_ASTAGES = 2;
-constexpr int TC_FLUSH = 4;
+constexpr int TC_RSTAGES = 4;   // raw A ring in shared memory, filled by TMA or cp.async (no register staging, no MSHR cap)
+constexpr int TC_ASTAGES = 2;   // A (activations) ring in TENSOR MEMORY, filled by tcgen05.st
+constexpr int TC_FLUSH = 4;     // K chunks accumulated in TMEM before the sum is flushed to registers
 #ifndef GAST_TC_CLUSTER
 #define GAST_TC_CLUSTER 2
 #endif
-constexpr int TC_CLUSTER = GAST_TC_CLUSTER;   // CTAs per cluster: same N tile, adjacent M tiles, B multicast by TMA     // K chunks accumulated in TMEM before the sum is flushed to registers   // A (activations) ring in TENSOR MEMORY, filled by tcgen05.st
+constexpr int TC_CLUSTER = GAST_TC_CLUSTER;   // CTAs per cluster: same N tile, adjacent M tiles, B multicast by TMA
 constexpr int TC_THREADS = 512;   // 4 warpgroups: A converters | epilogue (cols 0-63) | TMA, MMA, 1 idle | epilogue (cols 64-127)
 // registers per thread after setmaxnreg: A converters / epilogue groups / TMA+MMA warps (sum x 128 threads <= 64K)
 #ifndef GAST_TC_REG_A
@@ -69,7 +69,7 @@ static_assert(TC_REG_A + 2 * TC_REG_E + TC_REG_M <= 512, "register file over-sub
 constexpr int TC_PROBE_K = GAST_TC_PROBE_K;
 constexpr int TC_EN = 64;         // accumulator columns owned by one epilogue warpgroup
 constexpr int TC_STAGE_BYTES = 2 * 16384;            // B_hi, B_lo : 128 rows x 128 B each
-constexpr int TC_SLD = 68;                            // staging row stride (floats): conflict-free 16B rows
+constexpr int TC_SLD = 68;                            // SemCH coefficient slab row stride (floats): 64 channels + 4, conflict-free 16B rows
 constexpr int TC_MAX_NNZ = 64;    // SemCH coefficient slab rows
 constexpr int TC_MAXDEG = 6;      // SemCH: neighbours per joint kept in a packed register (17j: <= 5)
 constexpr int TC_JMAX = 20;
@@ -85,7 +85,7 @@ constexpr int TC_OFF_XPOSE = (TC_OFF_AB + 128 * 8 * 4 + 1023) / 1024 * 1024;  //
 constexpr int TC_OFF_BAR = TC_OFF_XPOSE + TC_RSTAGES * 128 * TC_XLD * 4;
 static_assert(TC_OFF_STAGING % 1024 == 0 && TC_OFF_XPOSE % 1024 == 0, "swizzled regions must be 1024-byte aligned");
 constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 256 + 1024;
-static_assert(TC_SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");   // 12 mbarriers + tmem ptr   // + alignment slack
+static_assert(TC_SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");   // 26 mbarriers + tmem ptr, + alignment slack
 
 // ----------------------------------------------------------------------------------------
 // PTX wrappers

@@ -47,18 +47,23 @@ __global__ void expand_kernel(const float* __restrict__ x, const float* __restri
   int j = (int)r0 - f * J;
   int b = f / T0;
   int t = f - b * T0;
+  // offset of (tap kk, feature i) = element k of the folded K axis, by increment as well (`k / Fin` with a
+  // runtime Fin inside the unrolled loops was 48 divisions per thread: half of the kernel's stall samples,
+  // profiles/r01_final_lines_expand.txt)
+  int xoff[KFT];
+  {
+    int kk = 0, i = 0;
+#pragma unroll
+    for (int k = 0; k < KFT; ++k) {
+      xoff[k] = kk * J * Fin + i;
+      if (++i == Fin) { i = 0; ++kk; }
+    }
+  }
 #pragma unroll
   for (int rr = 0; rr < EXP_ROWS; ++rr) {
     const float* xin = x + (((long long)b * T + (long long)t * stride) * J + j) * Fin;
 #pragma unroll
-    for (int k = 0; k < KFT; ++k) {
-      if (k < KF) {
-        const int kk = k / Fin, i = k - kk * Fin;
-        xv[rr][k] = __ldg(xin + (long long)kk * J * Fin + i);
-      } else {
-        xv[rr][k] = 0.f;
-      }
-    }
+    for (int k = 0; k < KFT; ++k) xv[rr][k] = (k < KF) ? __ldg(xin + xoff[k]) : 0.f;
     if (r0 + rr + 1 < rows) {                 // rows past the end re-read the last row
       if (++j == J) { j = 0; if (++t == T0) { t = 0; ++b; } }
     }
@@ -235,7 +240,8 @@ __global__ void tta_merge_kernel(const float* __restrict__ pred, float* __restri
 // 8 warps per SM can work on it and the mix is latency-bound there (ncu: tensor pipe 11 % busy, the
 // epilogue warps 97 % busy, profiles/r01_v19_lines_global.txt).  One thread = (frame, 4 channels): the 17
 // float4 of its channel group are read once (coalesced along the channel axis) and kept in registers, the
-// attention rows of the block's frames are computed once into shared memory.
+// attention rows of the block's frames are computed once into shared memory.  (A variant that requested the g values
+// before the attention rows and staged a/b in shared memory measured 6-17 % slower: more registers live across the barrier.)
 // ---------------------------------------------------------------------------------------
 constexpr int MIX_THREADS = 128;
 constexpr int MIX_JMAX = 20;

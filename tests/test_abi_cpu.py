@@ -98,3 +98,32 @@ def test_reference_checkpoint_layout_loads(tmp_path):
             assert torch.equal(a, b), k
     plain = SpatioTemporalModel(_adj(17), 17, 2, 17, [3, 3, 3], channels=16)
     plain.load_state_dict(torch.load(path.replace('m7', 'm0'))['model_pos'])      # reconstruction.py:239-240 verbatim
+
+
+def test_device_side_callers_have_no_cpu_path():
+    """The device-side counterparts of the caller modules (device/) import without a GPU, keep the reference's
+    names, and refuse CPU tensors instead of silently computing on the host."""
+    import numpy as np
+    import device.common.loss as L
+    import device.common.camera as Cm
+    import device.common.generators as Gn
+    import device.tools.mpii_coco_h36m as K
+    from gast_b200 import pipeline as P
+    from gast_b200.stream import PipelinedLifter
+    from model.gast_net import SpatioTemporalModel
+    for mod, names in ((L, ('mpjpe', 'p_mpjpe')), (Cm, ('normalize_screen_coordinates', 'image_coordinates', 'camera_to_world')),
+                       (Gn, ('ChunkedGenerator', 'UnchunkedGenerator')), (K, ('coco_h36m', 'mpii_h36m', 'coco_h36m_toe_format'))):
+        for n in names:
+            assert callable(getattr(mod, n)), n
+    a = torch.zeros(4, 1, 17, 3)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        L.mpjpe(a, a)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        P.keypoints_convert(torch.zeros(3, 17, 2), P.KPT_COCO_H36M)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        PipelinedLifter(SpatioTemporalModel(_adj(17), 17, 2, 17, [3, 3, 3], channels=16))
+    # the pair list and its shuffling are host logic shared with the oracle: identical to the reference's order
+    from oracle import pipeline_oracle as PO
+    pairs = PO.chunk_pairs((40, 7, 25), 1, True)
+    assert pairs.shape == (144, 4) and pairs[:, 3].sum() == 72
+    assert np.array_equal(pairs[:2], [[0, 0, 1, 0], [0, 1, 2, 0]]) and np.array_equal(pairs[40], [0, 0, 1, 1])
