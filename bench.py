@@ -315,7 +315,8 @@ def main():
         'gpu_launches': launches_per_step * K,
         'clocks': clocks,
         'roofline': {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                     'frac': achieved_tf / peak_tf, 'traffic': traffic,
+                     'frac': achieved_tf / peak_tf, 'frac_of_fp32_parity_bound': achieved_tf / (peak_tf / 6.0),
+                     'traffic': traffic,
                      'kernel': 'fused GEMM family (%d launches/step)' % prof['gemm_launches'],
                      'kernel_ms_per_step': gemm_ms, 'kernel_share_of_step': gemm_ms / prof['step_ms'],
                      'peak_source': 'bf16_tflops_sustained of %s MEASURED_PEAKS; fp32-parity 3xTF32 bound is peak/6'
