@@ -32,8 +32,8 @@ def val(r, name):
     return v
 
 
-print('| # | kernel | ' + ' | '.join(x[1] for x in cols) + ' |')
-print('|---|---|' + '---|' * len(cols))
+print('| # | kernel | ' + ' | '.join(x[1] for x in cols) + ' | DRAM GB/s |')
+print('|---|---|' + '---|' * (len(cols) + 1))
 tot_r = tot_w = tot_t = 0.0
 fam_r = fam_w = 0.0
 fam_n = 0
@@ -50,7 +50,8 @@ for i, r in enumerate(data):
     tot_t += val(r, 'gpu__time_duration.sum')
     tot_r += val(r, 'dram__bytes_read.sum')
     tot_w += val(r, 'dram__bytes_write.sum')
-    print('| %d | %s | ' % (i, epi) + ' | '.join(('%.0f' % v) if v >= 100 else ('%.1f' % v) for v in vals) + ' |')
+    gbs = (val(r, 'dram__bytes_read.sum') + val(r, 'dram__bytes_write.sum')) / val(r, 'gpu__time_duration.sum') * 1e3   # MB/us -> GB/s
+    print('| %d | %s | ' % (i, epi) + ' | '.join(('%.0f' % v) if v >= 100 else ('%.1f' % v) for v in vals) + ' | %.0f |' % gbs)
 print()
 print(json.dumps({'launches': len(data), 'sum_duration_us': tot_t, 'dram_read_MB': tot_r, 'dram_write_MB': tot_w,
                   'dram_bytes_per_step_all_kernels': (tot_r + tot_w) * 1e6,
