@@ -5,7 +5,6 @@ libgast_b200.so through the C ABI (include/gast_b200.h); the drop-in modules und
 `tools/` wrap them with the reference's own names and signatures.  No CPU path: a CPU tensor raises.
 """
 import ctypes as C
-import math
 
 import numpy as np
 import torch

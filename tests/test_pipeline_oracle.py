@@ -97,7 +97,6 @@ def test_oracle_vs_live_reference_random_configs():
     """Where the reference tree is present, drive its own ChunkedGenerator / converters on random configurations
     (short videos, long chunks, causal shifts, ragged last batch) and compare the oracle bit for bit."""
     import importlib.util
-    import sys
 
     def load(name, path):
         spec = importlib.util.spec_from_file_location(name, path)
