@@ -1,8 +1,8 @@
 """Device-resident versions of the steps either side of the lifting forward.
 
 Each function takes and returns CUDA float32 tensors and launches one small kernel of
-libgast_b200.so through the C ABI (include/gast_b200.h); the drop-in modules under `common/` and
-`tools/` wrap them with the reference's own names and signatures.  No CPU path: a CPU tensor raises.
+libgast_b200.so through the C ABI (include/gast_b200.h); the modules under `device/common/` and
+`device/tools/` wrap them with the reference's own names and signatures.  No CPU path: a CPU tensor raises.
 """
 import ctypes as C
 
