@@ -79,7 +79,10 @@ struct gast_handle {
   int nnz[2] = {0, 0};
   std::unordered_map<std::string, Binding> bound;
   std::unordered_map<std::string, Binding> grads;   // gradient outputs by state_dict key (training)
-  TrainState train;                                  // saved state of the last training forward
+  // saved-for-backward state of the training forwards still waiting for their backward, keyed by the
+  // caller's workspace (which holds the saved activations): several forwards may be outstanding
+  // (micro-batches summed before .backward(), a logging forward under no_grad in between)
+  std::vector<std::pair<void*, TrainState>> trains;
   std::vector<void*> owned;          // cudaMalloc'ed derived buffers
   std::vector<BlockConsts> blocks;
   std::vector<StageConsts> stages;
@@ -97,6 +100,8 @@ struct gast_handle {
   int fpt = 0;
   int sm_count = 148;
 };
+
+constexpr int GAST_MAX_PENDING_TRAIN = 16;   // training forwards that may wait for their backward per handle
 
 enum { LK_EXPAND = 0, LK_GEMM_PLAIN = 1, LK_GEMM_SEMCH = 2, LK_GEMM_GLOBAL = 3, LK_ROWDOT = 4, LK_SHRINK = 5,
        LK_TC_PLAIN = 6, LK_TC_SEMCH = 7, LK_TC_GLOBAL = 8, LK_GLOBAL_MIX = 9 };
@@ -582,13 +587,14 @@ static int launch_gemm(gast_handle* h, cudaStream_t st, int epi, const GemmP& p,
   int hpt = 1;
   if (epi == EPI_GLOBAL) hpt = p.heads < 4 ? p.heads : 4;
   size_t smem = ffma_smem_bytes(epi, p.J, p.fpt, hpt);
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[epi]) {
+  static bool attr_set_dev[64][3];          // the opt-in is per device (one handle per device in one process)
+  bool& attr_done = attr_set_dev[h->cfg.device & 63][epi];
+  if (!attr_done) {
     const void* fn = epi == EPI_PLAIN ? (const void*)gemm_ffma_kernel<EPI_PLAIN>
                    : epi == EPI_SEMCH ? (const void*)gemm_ffma_kernel<EPI_SEMCH>
                                       : (const void*)gemm_ffma_kernel<EPI_GLOBAL>;
     CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set[epi] = true;
+    attr_done = true;
   }
   if (epi == EPI_PLAIN) gemm_ffma_kernel<EPI_PLAIN><<<grid, FF_THREADS, smem, st>>>(p);
   else if (epi == EPI_SEMCH) gemm_ffma_kernel<EPI_SEMCH><<<grid, FF_THREADS, smem, st>>>(p);
@@ -921,8 +927,6 @@ extern "C" int gast_bind_grads(gast_t* h, int32_t n, const char* const* keys, vo
 
 static int train_check(gast_handle* h) {
   if (h->cfg.kind != GAST_KIND_MODEL) return fail("training is implemented for the MODEL kind only");
-  if (!h->cfg.strided) return fail("training runs the strided (Optimized1f) schedule only, like main.py:166-171; "
-                                   "construct SpatioTemporalModelOptimized1f for training");
   return 0;
 }
 
@@ -953,12 +957,16 @@ extern "C" int gast_forward_train(gast_t* h, const float* x, float* y, int32_t B
   if (need == 0) return 1;
   if (!workspace || workspace_bytes < need) return fail("gast_forward_train: workspace too small (%zu < %zu)", workspace_bytes, need);
   h->launches = 0;
-  h->train = TrainState();
-  h->train.drop_p = dropout_p;
-  h->train.seed = seed;
-  if (train_forward(h, c, h->train, x, y, B, T)) { h->train.valid = false; return 1; }
-  h->train.arena_off = a.off;
-  h->train.valid = true;
+  for (size_t i = 0; i < h->trains.size(); ++i)      // a workspace reused by the caller: its old state is dead
+    if (h->trains[i].first == workspace) { h->trains.erase(h->trains.begin() + i); break; }
+  if (h->trains.size() >= GAST_MAX_PENDING_TRAIN) h->trains.erase(h->trains.begin());   // forwards never differentiated
+  h->trains.emplace_back(workspace, TrainState());
+  TrainState& ts = h->trains.back().second;
+  ts.drop_p = dropout_p;
+  ts.seed = seed;
+  if (train_forward(h, c, ts, x, y, B, T)) { h->trains.pop_back(); return 1; }
+  ts.arena_off = a.off;
+  ts.valid = true;
   h->prepared = false;      // running statistics changed: eval constants are stale
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -966,16 +974,22 @@ extern "C" int gast_forward_train(gast_t* h, const float* x, float* y, int32_t B
 
 extern "C" int gast_backward(gast_t* h, const float* dy, void* workspace, size_t workspace_bytes, void* stream) {
   if (!h) return fail("gast_backward: null handle");
-  if (!h->train.valid) return fail("gast_backward: no training forward to differentiate");
+  size_t ti = h->trains.size();
+  for (size_t i = 0; i < h->trains.size(); ++i)
+    if (h->trains[i].first == workspace) ti = i;
+  if (ti == h->trains.size() || !h->trains[ti].second.valid)
+    return fail("gast_backward: no training forward is saved in this workspace (already differentiated, "
+                "or more than %d forwards were outstanding)", GAST_MAX_PENDING_TRAIN);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUDA_OK(cudaSetDevice(h->cfg.device));
   uintptr_t wsb = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
-  Arena a{reinterpret_cast<char*>(wsb), workspace_bytes, h->train.arena_off, false};
+  TrainState ts = h->trains[ti].second;
+  h->trains.erase(h->trains.begin() + ti);
+  Arena a{reinterpret_cast<char*>(wsb), workspace_bytes, ts.arena_off, false};
   Lookup L{h};
   TCtx c{h, st, &a, &L, h->cfg.num_joints, false};
-  if (train_backward(h, c, h->train, dy)) return 1;
+  if (train_backward(h, c, ts, dy)) return 1;
   if (a.off > workspace_bytes) return fail("gast_backward: workspace overrun");
-  h->train.valid = false;
   CUDA_OK(cudaGetLastError());
   return 0;
 }

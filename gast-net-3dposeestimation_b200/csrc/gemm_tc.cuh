@@ -1224,12 +1224,14 @@ inline int tc_launch_one(int grid, cudaStream_t st, const GemmP& p_in, const TcW
   TcAMaps am;
   tc_build_amaps(p, am);
   if (!am.ok) { am.m[0] = t.map_hi; am.m[1] = t.map_hi; am.m[2] = t.map_hi; }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64];                 // the shared-memory opt-in is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute((const void*)gemm_tc_kernel<EPI, DBG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_set[dev & 63] = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

@@ -6,8 +6,8 @@
 // Everything a backward needs is kept in the caller's workspace (bump allocation, no reuse): the
 // training batch is small (b=128 -> 19,584 / 6,528 / 2,176 rows), so memory is not the constraint.
 // Dense contractions run on the FFMA GEMM kernel (exact fp32); the frame-mapped operands of the
-// temporal stages are gathered exactly as in inference.  Only the strided (Optimized1f) schedule is
-// supported in training, like the reference's training path (main.py:166-171).
+// temporal stages are gathered exactly as in inference.  Both schedules train: the strided one of
+// SpatioTemporalModelOptimized1f (main.py:166-170) and the dilated one of SpatioTemporalModel (main.py:171-175).
 #pragma once
 
 // ---------------------------------------------------------------------------------------------
@@ -345,9 +345,14 @@ static int block_bwd(TCtx& c, BlockSave& b, BlockConsts& bc, const float* dOut, 
 static int train_forward(gast_handle* h, TCtx& c, TrainState& ts, const float* x, float* y, int B, int T) {
   const gast_cfg& cf = h->cfg;
   const int J = c.J, C = cf.channels, L = cf.num_stages, Fin = cf.in_features, k0 = cf.filter_widths[0];
+  // schedule = the handle's own: strided for SpatioTemporalModelOptimized1f (main.py:166-170), dilated (or the
+  // dense ablation) for SpatioTemporalModel (main.py:171-175, `--disable-optimizations` / stride > 1).  Batch
+  // statistics are taken over every position the reference computes, so a dilated model never runs the
+  // needed-only schedule in training.
+  const int sn = cf.strided ? 1 : 0;
   Geometry g;
-  if (geometry(h, T, 1, &g)) return 1;
-  ts.B = B; ts.T = T; ts.T0 = g.T0; ts.x = x;
+  if (geometry(h, T, sn, &g)) return 1;
+  ts.B = B; ts.T = T; ts.T0 = g.T0; ts.s0 = g.s0; ts.x = x;
   ts.blocks.assign(L, BlockSave());
   ts.stages.assign(L - 1, StageSave());
   const RowMap id{1, 1, 1, 0};
@@ -366,7 +371,7 @@ static int train_forward(gast_handle* h, TCtx& c, TrainState& ts, const float* x
     cudaMemsetAsync(ts.Acol, 0, sizeof(float) * (size_t)M0 * KP, c.st);
     cudaMemsetAsync(ts.We8, 0, sizeof(float) * (size_t)C * KP, c.st);
     ASeg sg; sg.base = ts.xbn; sg.ld = Fin; sg.K = k0 * Fin; sg.Kc = Fin; sg.tap_stride = (long long)J * Fin;
-    sg.map = RowMap{g.T0, T, k0, 0};
+    sg.map = RowMap{g.T0, T, g.s0, 0};
     seg_gather_kernel<<<cdiv(M0 * sg.K, 256), 256, 0, c.st>>>(sg, J, F0, ts.Acol, KP, 0);
     BnP none{nullptr, nullptr, nullptr, nullptr};
     // We8[c][tap*Fin + i] = w[c][i][tap]  (fold_conv_kernel with no BN is exactly this re-layout)
@@ -385,7 +390,7 @@ static int train_forward(gast_handle* h, TCtx& c, TrainState& ts, const float* x
   for (int i = 1; i < L; ++i) {
     StageSave& s = ts.stages[i - 1];
     Sched sc;
-    stage_sched(h, i, 1, &sc);
+    stage_sched(h, i, sn, &sc);
     const int Cw = C << i, Tn = g.Ts[i - 1];
     const long long Fn = (long long)B * Tn, Mn = Fn * J;
     s.Cw = Cw; s.taps = sc.taps; s.Fin = F; s.Fout = Fn; s.Tin = Tp; s.Tout = Tn; s.X = cur; s.idx = i - 1; s.dil = sc.dil;
@@ -505,7 +510,7 @@ static int train_backward(gast_handle* h, TCtx& c, TrainState& ts, const float* 
     conv_wgrad_relayout_kernel<<<cdiv((long long)C * Fin * k0, 256), 256, 0, c.st>>>(dWe8, C, Fin, k0, KP, gwe);
     cudaMemsetAsync(dxbn, 0, sizeof(float) * (size_t)Min * Fin, c.st);
     ASeg sg; sg.base = dxbn; sg.ld = Fin; sg.K = k0 * Fin; sg.Kc = Fin; sg.tap_stride = (long long)J * Fin;
-    sg.map = RowMap{ts.T0, ts.T, k0, 0};
+    sg.map = RowMap{ts.T0, ts.T, ts.s0, 0};
     seg_scatter_add_kernel<<<cdiv(M0 * sg.K, 256), 256, 0, c.st>>>(sg, J, F0, dAcol, KP, 0);
   }
   if (bn_bwd(c, ts.bnin, dxbn, Fin, dxin, Fin)) return 1;

@@ -33,7 +33,7 @@ struct StageSave {
 
 struct TrainState {
   bool valid = false;
-  int B = 0, T = 0, T0 = 0;
+  int B = 0, T = 0, T0 = 0, s0 = 1;   // s0: stride of the expand conv (filter width when strided, else 1)
   const float* x = nullptr;
   float *xbn = nullptr, *Acol = nullptr, *We8 = nullptr, *Z0 = nullptr, *act0 = nullptr;
   BnSave bnin, bnex;

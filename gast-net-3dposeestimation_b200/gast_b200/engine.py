@@ -42,6 +42,54 @@ def _m2d(m):
     return m[0] if m.dim() == 3 else m
 
 
+def named_tensors(module):
+    """(key, tensor) pairs under the names `module.state_dict()` uses, in its order.  Unlike state_dict() this
+    also works on the per-forward replicas of nn.DataParallel (trainval.py:56-61), whose weights are broadcast
+    views kept as plain attributes (`_former_parameters`) instead of in `_parameters`."""
+    out = []
+    for prefix, mod in module.named_modules():
+        pre = prefix + '.' if prefix else ''
+        former = getattr(mod, '_former_parameters', None) or {}
+        for k, v in mod._parameters.items():
+            if v is not None:
+                out.append((pre + k, v))
+        for k, v in former.items():
+            if v is not None and mod._parameters.get(k) is None:
+                out.append((pre + k, v))
+        for k, v in mod._buffers.items():
+            if v is not None and k not in mod._non_persistent_buffers_set:
+                out.append((pre + k, v))
+    return out
+
+
+def named_params(module):
+    """named_parameters() that also sees the broadcast parameter views of a DataParallel replica
+    (they are non-leaf tensors connected to the real parameters, so autograd routes the gradients)."""
+    out = []
+    for prefix, mod in module.named_modules():
+        pre = prefix + '.' if prefix else ''
+        former = getattr(mod, '_former_parameters', None) or {}
+        for k, v in mod._parameters.items():
+            if v is not None:
+                out.append((pre + k, v))
+        for k, v in former.items():
+            if v is not None and mod._parameters.get(k) is None:
+                out.append((pre + k, v))
+    return out
+
+
+class _HandleStore(dict):
+    """device -> _Handle, kept in the module's __dict__ (so that the shallow-copied replicas of
+    nn.DataParallel share it).  Native handles are per process and per device: a deepcopy / pickle of the
+    module (EMA copies, torch.save(model)) gets an empty store and builds its own handles on first use."""
+
+    def __deepcopy__(self, memo):
+        return _HandleStore()
+
+    def __reduce__(self):
+        return (_HandleStore, ())
+
+
 class _Handle(object):
     def __init__(self, module, kind, device, cfg_kw, sym=None, con=None):
         lib = L.load()
@@ -83,7 +131,7 @@ class _Handle(object):
 
     def refresh(self, module, stream):
         """(re)bind + prepare when any parameter/buffer moved or changed."""
-        items = [(k, v) for k, v in module.state_dict(keep_vars=True).items()]
+        items = named_tensors(module)
         sig = tuple((v.data_ptr(), v._version) for _, v in items)
         if _FORCE_CORE['core'] != self.core:
             _check(self.lib.gast_set_gemm_core(self.h, _FORCE_CORE['core']), 'gast_set_gemm_core')
@@ -109,7 +157,7 @@ class _Handle(object):
 
     def bind_only(self, module):
         """bind parameter/buffer storage without the eval-mode prepare (training path)"""
-        items = [(k, v) for k, v in module.state_dict(keep_vars=True).items()]
+        items = named_tensors(module)
         n = len(items)
         keys = (C.c_char_p * n)()
         ptrs = (C.c_void_p * n)()
@@ -148,7 +196,9 @@ def _require_cuda(x, what):
 
 
 def _handle_for(module, device, factory):
-    store = module.__dict__.setdefault('_gast_handles', {})
+    store = module.__dict__.get('_gast_handles')
+    if store is None:
+        store = module.__dict__.setdefault('_gast_handles', _HandleStore())
     key = (device.type, device.index)
     h = store.get(key)
     if h is None:
@@ -177,7 +227,7 @@ class _TrainFn(torch.autograd.Function):
             if need == 0:
                 raise GastError('gast_train_workspace_bytes: %s' % L.last_error())
             ws = torch.empty(int(need), dtype=torch.uint8, device=dev)
-            T_out = lib.gast_out_frames(handle.h, T, 1)
+            T_out = lib.gast_out_frames(handle.h, T, 1 if module._gast_strided else 0)
             if T_out <= 0:
                 raise GastError('forward: %s' % L.last_error())
             y = torch.empty((B, T_out, module.num_joints_in, 3), dtype=torch.float32, device=dev)
@@ -228,8 +278,9 @@ class _TrainFn(torch.autograd.Function):
 
 def _no_train(module, what):
     if module.training:
-        raise GastError('%s: training-mode forward/backward is not built yet in this round; '
-                        'call .eval() (no silent fallback is provided)' % what)
+        raise GastError('%s: the training-mode forward/backward exists for the whole model only '
+                        '(SpatioTemporalModel / SpatioTemporalModelOptimized1f, what main.train() drives); a sub-module '
+                        'on its own runs in eval mode -- call .eval() (there is no silent fallback)' % what)
 
 
 # ------------------------------------------------------------------------------------------
@@ -249,11 +300,11 @@ def run_model(module, x):
     x = x.contiguous()
     B, T = int(x.shape[0]), int(x.shape[1])
     if module.training:
-        if not module._gast_strided:
-            raise GastError('training runs on SpatioTemporalModelOptimized1f (strided schedule), which is what '
-                            'the reference trains with (main.py:166-171); the dilated model is eval-only here')
-        names = [k for k, _ in module.named_parameters()]
-        params = [p for _, p in module.named_parameters()]
+        # both of the reference's training models: Optimized1f (main.py:166-170) and, with
+        # --disable-optimizations / stride > 1, the dilated SpatioTemporalModel (main.py:171-175)
+        np_ = named_params(module)
+        names = [k for k, _ in np_]
+        params = [p for _, p in np_]
         y = _TrainFn.apply(module, h, x, names, *params)
         module.__dict__['_gast_last_launches'] = h.launches()
         return y

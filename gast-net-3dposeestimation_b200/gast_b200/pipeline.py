@@ -238,6 +238,9 @@ class FusedAdam(object):
                                            _p(self.max_exp_avg_sq), float(g['lr']), float(g['betas'][0]),
                                            float(g['betas'][1]), float(g['eps']), float(g['weight_decay']),
                                            self.step_count, C.c_void_p(_stream(dev))), 'gast_adam_step')
+        # the kernel writes the parameters through raw pointers: bump their version counters so that everything
+        # keyed on (data_ptr, _version) -- the engine's folded eval-mode constants -- sees the update
+        torch.autograd.graph.increment_version(self.params)
 
     def state_dict(self):
         return {'step': self.step_count, 'exp_avg': self.exp_avg, 'exp_avg_sq': self.exp_avg_sq,

@@ -17,6 +17,24 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
 
 
+def pytest_collection_modifyitems(config, items):
+    """`-m gpu` tests need a CUDA device and the built library; without them they are skipped (not failed),
+    so that a plain `pytest tests` is green on a CPU-only machine."""
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    lib = os.path.join(PKG, 'csrc', 'libgast_b200.so')
+    if have and os.path.exists(lib):
+        return
+    why = 'no CUDA device' if not have else 'libgast_b200.so is not built'
+    skip = pytest.mark.skip(reason='gpu test: ' + why)
+    for it in items:
+        if 'gpu' in it.keywords:
+            it.add_marker(skip)
+
+
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN, name + '.npz'))
     d = {k: z[k] for k in z.files if k != 'meta'}

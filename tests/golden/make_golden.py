@@ -250,6 +250,90 @@ def module_cases():
          meta=dict(kind='block', J=J2, C=16, seed=9, keys=keys_shapes(blk2)))
 
 
+def _digest(t, idx):
+    """compact fingerprint of one tensor: norm, sum, and the entries at `idx` (flat indices)"""
+    f = t.detach().reshape(-1).double()
+    return np.array([float(f.norm()), float(f.sum())], np.float64), f[idx].numpy().astype(np.float32)
+
+
+def train_case(name, J, fw, ch, B, nsteps, full_grads, dilated=False, seed=9):
+    """a12 / BASELINE configs[2] golden: the UNMODIFIED reference model in train() mode, dropout 0, driven exactly
+    as main.train() drives it (main.py:219-239: root joint of the target zeroed, zero_grad, forward, mpjpe,
+    backward, optimizer.step) with optim.Adam(lr=1e-3, amsgrad=True) (trainval.py:78).  Stored per step: the
+    prediction, the loss, and per parameter either the whole gradient (small cases) or its norm, sum and 48
+    entries at the flat indices where |grad of step 0| is largest (those are far above the fp32 gradient noise);
+    after the last step: every BatchNorm running statistic and the same fingerprint of every parameter."""
+    from common.loss import mpjpe
+    adj = adj_for(J)
+    T = int(np.prod(fw))
+    if dilated:
+        m = SpatioTemporalModel(adj, J, 2, J, fw, dropout=0.0, channels=ch)
+    else:
+        m = SpatioTemporalModelOptimized1f(adj, J, 2, J, fw, dropout=0.0, channels=ch)
+    synth.randomize_module(m, seed)
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, amsgrad=True)
+    names = [k for k, _ in m.named_parameters()]
+    out = {}
+    idx = {}
+    with torch.enable_grad():
+        for step in range(nsteps):
+            x = torch.from_numpy(synth.synth_input(B, T, J, 2, seed=100 + step))
+            tgt = torch.from_numpy(synth.synth_target(B, J, seed=200 + step))
+            tgt[:, :, 0] = 0                                     # main.py:225
+            opt.zero_grad()
+            y = m(x)
+            loss = mpjpe(y, tgt)
+            loss.backward()
+            out['y%d' % step] = y.detach().contiguous().numpy().copy()
+            out['loss%d' % step] = np.array(loss.item(), np.float64)
+            for k, prm in m.named_parameters():
+                g = prm.grad.detach().reshape(-1)
+                if step == 0:
+                    n = min(48, g.numel())
+                    idx[k] = torch.topk(g.abs(), n).indices.sort().values
+                    out['idx/' + k] = idx[k].numpy().astype(np.int64)
+                if full_grads and step == 0:
+                    out['grad0/' + k] = prm.grad.detach().numpy().copy()
+                ns, ent = _digest(prm.grad, idx[k])
+                out['gsum%d/%s' % (step, k)] = ns
+                out['gent%d/%s' % (step, k)] = ent
+            opt.step()
+    for k, prm in m.named_parameters():
+        ns, ent = _digest(prm, idx[k])
+        out['psum/' + k] = ns
+        out['pent/' + k] = ent
+    for k, v in m.state_dict().items():
+        if 'running_' in k or 'num_batches' in k:
+            out['stat/' + k] = v.numpy().copy()
+    meta = dict(kind='train', J=J, filter_widths=fw, channels=ch, B=B, T=T, nsteps=nsteps, seed=seed, dilated=dilated,
+                names=names, full_grads=full_grads, lr=1e-3, amsgrad=True)
+    save(name, meta=meta, **out)
+
+
+def train_cases():
+    train_case('train_17_333_c32_b6', 17, [3, 3, 3], 32, 6, 2, full_grads=True)
+    train_case('train_19_33_c32_b5', 19, [3, 3], 32, 5, 1, full_grads=True)
+    train_case('train_17_333_c16_dilated_b4', 17, [3, 3, 3], 16, 4, 1, full_grads=True, dilated=True)
+    # BASELINE configs[2] at its real size: -arc 3,3,3 -ch 128 -b 128, three Adam(amsgrad) steps
+    train_case('train_cfg3_17_333_c128_b128', 17, [3, 3, 3], 128, 128, 3, full_grads=False)
+
+
+def tc_cases():
+    """widths that are multiples of 32, so that the tcgen05 GEMM core (K % 32 == 0) sees every skeleton and
+    geometry: J = 15 / 16 / 19, five stages (243 frames, reconstruction.py:226-228), the dense ablation, a
+    two-stage model with a 5-wide filter, causal + long-sequence (dilated) mode"""
+    model_case('tc_15_333_c32_full_T29', 15, [3, 3, 3], 32, 2, 29, strided=False)
+    model_case('tc_16_333_c32_full_T27', 16, [3, 3, 3], 32, 3, 27, strided=False)
+    model_case('tc_19_333_c32_1f_T27', 19, [3, 3, 3], 32, 3, 27, strided=True)
+    model_case('tc_17_33333_c32_1f_T243', 17, [3, 3, 3, 3, 3], 32, 1, 243, strided=True)
+    model_case('tc_17_33333_c32_full_T245', 17, [3, 3, 3, 3, 3], 32, 1, 245, strided=False)
+    model_case('tc_17_333_c32_dense_T28', 17, [3, 3, 3], 32, 2, 28, strided=False, dense=True)
+    model_case('tc_17_35_c32_full_T17', 17, [3, 5], 32, 2, 17, strided=False)
+    model_case('tc_17_333_c32_causal_full_T40', 17, [3, 3, 3], 32, 2, 40, strided=False, causal=True)
+    model_case('tc_17_3333_c64_causal_full_T90', 17, [3, 3, 3, 3], 64, 1, 90, strided=False, causal=True)
+
+
 def main():
     torch.manual_seed(0)
     module_cases()
@@ -265,6 +349,7 @@ def main():
     model_case('model_19_333_c16_full_T29', 19, [3, 3, 3], 16, 2, 29, strided=False)
     model_case('model_17_35_c8_full_T17', 17, [3, 5], 8, 2, 17, strided=False)
     model_case('model_17_33333_c8_1f_T243', 17, [3, 3, 3, 3, 3], 8, 1, 243, strided=True)
+    tc_cases()
     # BASELINE.json configs at full width, small batch
     model_case('cfg2_17_333_c128_full_T27', 17, [3, 3, 3], 128, 4, 27, strided=False)
     model_case('cfg2_17_333_c128_full_T40', 17, [3, 3, 3], 128, 1, 40, strided=False)
@@ -280,7 +365,12 @@ if __name__ == '__main__':
         tta_cases()
     elif len(sys.argv) > 1 and sys.argv[1] == 'pipeline':
         pipeline_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'train':
+        train_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'tc':
+        tc_cases()
     else:
         main()
         tta_cases()
         pipeline_cases()
+        train_cases()

@@ -1,11 +1,25 @@
 """Training path (BASELINE configs[2]) on the GPU against the torch-CPU port of
 the reference under autograd: train-mode forward (batch-stat BN, running-stat update), every
 parameter gradient, and a 3-step Adam(amsgrad) loop with loss / state_dict match (dropout 0)."""
+import os
 import numpy as np
 import pytest
 import torch
 
+from conftest import load_golden, golden_names
 from gast_b200 import synth
+import train_fixture as TF
+
+REPORT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+
+
+def _report(name, lines):
+    try:
+        os.makedirs(REPORT_DIR, exist_ok=True)
+        with open(os.path.join(REPORT_DIR, name), 'a') as f:
+            f.write('\n'.join(lines) + '\n')
+    except OSError:
+        pass
 
 pytestmark = pytest.mark.gpu
 
@@ -62,8 +76,14 @@ def test_train_forward_and_gradients(J, fw, ch, B):
     for k, v in stats.items():
         assert (sd1[k].cpu() - v).abs().max().item() < 1e-5 * max(1.0, float(v.abs().max())), k
     assert int(sd1['init_bn.num_batches_tracked']) == 1
-    # every parameter gradient
+    # every parameter gradient.  fp32 gradients of this net are chaotic at the 1e-3..1e-2 level (a BatchNorm
+    # output that lands on the other side of zero flips a ReLU and changes the gradient discretely), so the
+    # bar is the reference's OWN fp32 noise against fp64: in aggregate (all gradients concatenated, and the
+    # median per-tensor ratio) the CUDA path must be within 2x of it; per tensor, where single flips dominate,
+    # within 4x or an absolute floor.
     bad = []
+    num_c = num_r = den = 0.0
+    ratios = []
     for k, prm in m.named_parameters():
         assert prm.grad is not None, k
         g, gd = prm.grad.cpu().double(), pd[k].grad
@@ -75,9 +95,16 @@ def test_train_forward_and_gradients(J, fw, ch, B):
         g32 = p[k].grad.double()                      # the reference port's own fp32 gradient
         l2_ref = ((g32 - gd).norm() / gd.norm()).item()
         mx_ref = ((g32 - gd).abs().max() / gd.abs().max()).item()
-        # as accurate as the reference's fp32 arithmetic (x4 slack), or better than 1e-2 / 3e-2
-        if not (l2 < max(1e-2, 4 * l2_ref) and mx < max(3e-2, 4 * mx_ref)):
+        num_c += float((g - gd).norm() ** 2); num_r += float((g32 - gd).norm() ** 2); den += float(gd.norm() ** 2)
+        ratios.append(l2 / max(l2_ref, 1e-7))
+        if not (l2 < max(5e-3, 4 * l2_ref) and mx < max(2e-2, 4 * mx_ref)):
             bad.append((k, round(l2, 5), round(l2_ref, 5), round(mx, 5), round(mx_ref, 5)))
+    agg_c, agg_r = (num_c / den) ** 0.5, (num_r / den) ** 0.5
+    med = float(np.median(ratios))
+    _report('train_grad_noise.txt', ['J=%d fw=%s ch=%d B=%d: all-gradient rel. L2 error vs fp64: cuda %.3e, reference fp32 %.3e; '
+                                     'median per-tensor ratio %.2f; per-tensor outliers %d' % (J, fw, ch, B, agg_c, agg_r, med, len(bad))])
+    assert agg_c <= 2.0 * agg_r + 1e-6, (agg_c, agg_r)
+    assert med <= 2.0, med
     assert not bad, sorted(bad, key=lambda t: -t[1])[:12]
 
 
@@ -166,6 +193,121 @@ def test_dropout_and_mode_errors():
     assert torch.equal(y1, y2) and not torch.equal(y1, y3)      # dropout stream follows torch's seed
     y1.sum().backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
-    d = SpatioTemporalModel(_adj(17), 17, 2, 17, [3, 3, 3], channels=32).cuda().train()
-    with pytest.raises(RuntimeError, match='Optimized1f'):
-        d(x)
+    # a sub-module on its own has no training path: loud error, no fallback
+    from model.local_attention import LocalGraph
+    lg = LocalGraph(_adj(17), 32, 32, 0.1).cuda().train()
+    with pytest.raises(RuntimeError, match='eval'):
+        lg(torch.zeros(2, 3, 17, 32, device='cuda'))
+
+
+@pytest.mark.parametrize('name', golden_names('train_'))
+def test_training_vs_reference_fixture(name):
+    """a12 / BASELINE configs[2] against fixtures of the UNMODIFIED reference (tests/golden/make_golden.py:
+    train_case): main.train()'s loop (main.py:219-239) with Adam(amsgrad) (trainval.py:78), dropout 0.
+    `train_cfg3_17_333_c128_b128` is the configuration as specified: -arc 3,3,3, 128 channels, b = 128, three
+    steps, loss to 1e-5 relative.  The dilated case is main.py:171-175's training model."""
+    g = load_golden(name)
+    meta = g['meta']
+    m = TF.build_module(meta).cuda().train()
+    opt = torch.optim.Adam(m.parameters(), lr=meta['lr'], amsgrad=meta['amsgrad'])
+    rep = ['== ' + name]
+    for step in range(meta['nsteps']):
+        x, tgt = TF.batch(meta, step)
+        opt.zero_grad()
+        y = m(x.cuda())
+        loss = torch.mean(torch.norm(y - tgt.cuda(), dim=3))
+        loss.backward()
+        TF.check_step(g, step, y.detach().cpu().numpy(), loss.item(), {k: p.grad for k, p in m.named_parameters()},
+                      y_tol=5e-5, loss_rtol=1e-5, ent_rtol=3e-2, norm_rtol=3e-2, report=rep)
+        opt.step()
+    sd = m.state_dict()
+    worst = 0.0
+    for k in meta['names']:
+        if float(g['gsum0/' + k][0]) < 1e-12:
+            continue                                      # zero-gradient parameter: Adam moves it by noise
+        _, ent = TF.digest(sd[k], g['idx/' + k])
+        d = float(np.abs(ent - g['pent/' + k]).max())
+        worst = max(worst, d)
+        assert d < 2e-5, (k, d)                           # parameters after the Adam steps, at the large-|g| entries
+    for k in sd:
+        if 'running_' in k:
+            ref = g['stat/' + k]
+            assert np.abs(sd[k].cpu().numpy() - ref).max() < 1e-4 * max(1.0, np.abs(ref).max()), k
+        if 'num_batches' in k:
+            assert int(sd[k]) == int(g['stat/' + k])
+    rep.append('post-step parameters: max |delta| at the fingerprint entries %.3g' % worst)
+    _report('train_fixture_report.txt', rep)
+
+
+def test_two_forwards_before_backward_and_no_grad_forward():
+    """several training forwards of one module may be outstanding (micro-batches summed before .backward(), a
+    logging forward under no_grad in between): each backward differentiates its own forward."""
+    from model.gast_net import SpatioTemporalModelOptimized1f
+    m = SpatioTemporalModelOptimized1f(_adj(17), 17, 2, 17, [3, 3, 3], dropout=0.0, channels=32)
+    synth.randomize_module(m, 3)
+    m = m.cuda().train()
+    xa = torch.from_numpy(synth.synth_input(4, 27, 17, 2, seed=1)).cuda()
+    xb = torch.from_numpy(synth.synth_input(6, 27, 17, 2, seed=2)).cuda()
+
+    def grads(x):
+        m.zero_grad()
+        m(x).square().sum().backward()
+        return [p.grad.clone() for p in m.parameters()]
+    ga, gb = grads(xa), grads(xb)
+    m.zero_grad()
+    ya = m(xa)
+    with torch.no_grad():
+        m(xb)                                             # logging forward: replaces nothing
+    yb = m(xb)
+    (ya.square().sum() + yb.square().sum()).backward()
+    for p, a, b in zip(m.parameters(), ga, gb):
+        assert torch.allclose(p.grad, a + b, rtol=1e-4, atol=1e-6 * float((a + b).abs().max() + 1e-30))
+
+
+def test_model_copies_and_fused_adam_refresh():
+    """deepcopy / pickling of a module that already ran (EMA, best-model snapshots) works, and FusedAdam's raw
+    pointer updates are seen by the cached eval-mode constants."""
+    import copy
+    import io
+    from model.gast_net import SpatioTemporalModelOptimized1f
+    from gast_b200.pipeline import FusedAdam
+    m = SpatioTemporalModelOptimized1f(_adj(17), 17, 2, 17, [3, 3, 3], dropout=0.0, channels=32)
+    synth.randomize_module(m, 3)
+    m = m.cuda().eval()
+    x = torch.from_numpy(synth.synth_input(4, 27, 17, 2, seed=1)).cuda()
+    with torch.no_grad():
+        y0 = m(x)
+        m2 = copy.deepcopy(m)
+        assert torch.equal(m2(x), y0)
+        buf = io.BytesIO()
+        torch.save(m, buf)
+    opt = FusedAdam(m.parameters(), lr=1e-2, amsgrad=True)
+    m.train()
+    m(x).square().sum().backward()
+    opt.step()
+    m.eval()
+    with torch.no_grad():
+        y1 = m(x)
+        assert (y1 - y0).abs().max().item() > 1e-4        # the step is visible
+        assert torch.equal(m2(x), y0)                     # the copy kept its own weights and handle
+
+
+def test_fused_adam_invalidates_bn_free_submodule_constants():
+    """SemCHGraphConv has no BatchNorm whose buffers would change: only the version bump of FusedAdam.step
+    tells the engine that the softmaxed adjacency / packed weights are stale."""
+    from model.local_attention import SemCHGraphConv, local_adjacencies
+    from gast_b200.pipeline import FusedAdam
+    _, con = local_adjacencies(_adj(17))
+    sc = SemCHGraphConv(32, 32, con)
+    synth.randomize_module(sc, 7)
+    sc = sc.cuda()
+    x = torch.randn(2, 3, 17, 32, device='cuda')
+    with torch.no_grad():
+        y0 = sc(x)
+    opt = FusedAdam(sc.parameters(), lr=1e-1)
+    for p in sc.parameters():
+        p.grad = torch.ones_like(p)
+    opt.step()
+    with torch.no_grad():
+        y1 = sc(x)
+    assert (y1 - y0).abs().max().item() > 1e-3

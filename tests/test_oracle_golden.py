@@ -144,3 +144,44 @@ def test_tta_restatement_matches_reference_generator():
     assert np.array_equal(O.tta_merge(g['pred'], left, right), g['merged'][0])
     b = load_golden('cfg1_baseball_17_333_c128')['x']
     assert np.array_equal(O.tta_prepare(b[0, 13:-13], 13, 0, left, right), b)
+
+
+# ---------------------------------------------------------------------------------------------
+# training mode: the differentiable torch port against fixtures of the UNMODIFIED reference
+# (forward, mpjpe, every gradient, Adam(amsgrad) steps, running statistics)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', golden_names('train_'))
+def test_torch_ref_training_matches_reference_fixture(name):
+    import torch
+    from oracle import gast_torch_ref as TR
+    import train_fixture as TF
+    g = load_golden(name)
+    meta = g['meta']
+    if meta['B'] >= 128 and meta['nsteps'] > 1:
+        nsteps = 2                     # CPU CI time: the third step of the b=128 case is checked on the GPU path
+    else:
+        nsteps = meta['nsteps']
+    m = TF.build_module(meta)
+    p = {k: v.clone().requires_grad_(v.dtype.is_floating_point and 'running' not in k)
+         for k, v in m.state_dict().items()}
+    masks = tuple(torch.from_numpy(a) for a in O.local_masks(adj_for(meta['J'])))
+    opt = torch.optim.Adam([p[k] for k in meta['names']], lr=meta['lr'], amsgrad=meta['amsgrad'])
+    stats = {}
+    for step in range(nsteps):
+        x, tgt = TF.batch(meta, step)
+        opt.zero_grad()
+        y = TR.forward(x, p, masks, meta['filter_widths'], strided=not meta['dilated'], training=True, stats=stats)
+        loss = TR.mpjpe(y, tgt)
+        loss.backward()
+        # same ATen kernels in the same order as the reference modules: agreement is at rounding level
+        TF.check_step(g, step, y.detach().numpy(), loss.item(), {k: p[k].grad for k in meta['names']},
+                      y_tol=2e-6, loss_rtol=1e-6, ent_rtol=2e-3, norm_rtol=2e-3)
+        if meta['full_grads'] and step == 0:
+            for k in meta['names']:
+                gr = g['grad0/' + k]
+                if np.abs(gr).max() > 1e-12:
+                    assert np.abs(p[k].grad.numpy() - gr).max() <= 2e-3 * np.abs(gr).max(), k
+        opt.step()
+    if nsteps == meta['nsteps']:
+        for k, v in stats.items():
+            assert np.abs(v.numpy() - g['stat/' + k]).max() < 1e-5 * max(1.0, np.abs(g['stat/' + k]).max()), k
