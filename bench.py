@@ -36,6 +36,17 @@ J, FW, CH, T = 17, [3, 3, 3], 128, 27
 FLOP_PER_CLIP = 0.402e9          # algorithmic (needed-only) forward FLOPs, BASELINE.md §2
 IO_BYTES_PER_CLIP = 3876         # compulsory (T*J*2 + J*3)*4 bytes
 
+# The other BASELINE.json configurations, reported in `other_configs` after the headline (configs[1]) region.
+# flop = algorithmic (needed-only) FLOPs per clip; `global_clips` is split over the ranks
+# (strong scaling, as BASELINE.json words them: "batch 2048 clip-sharded across 8", "batch 8192, 2/4/8 sweep").
+OTHER = {
+    'cfg4_81f_17j_64ch': dict(J=17, fw=[3, 3, 3, 3], ch=64, T=81, flop=0.490e9, global_clips=2048,
+                              what='BASELINE configs[3]: 81-frame (-arc 3,3,3,3) 17-joint inference, 64 channels'),
+    'cfg5_27f_19j_128ch': dict(J=19, fw=[3, 3, 3], ch=128, T=27, flop=0.451e9, global_clips=8192,
+                               what='BASELINE configs[4]: 27-frame 19-joint body+toe inference, 128 channels'),
+}
+TRAIN_FLOP_PER_CLIP = 1.21e9     # fwd + bwd, SURVEY.md §8(d)
+
 
 def measured_peaks():
     p = os.path.join(REPO, 'MEASURED_PEAKS.json')
@@ -89,16 +100,155 @@ class ClockSampler(threading.Thread):
                 'samples': len(sm)}
 
 
-def build_model(device):
+def build_model(device, J_=J, fw=FW, ch=CH, cls='full', dropout=0.05):
     import torch
     from gast_b200 import synth
-    from model.gast_net import SpatioTemporalModel
+    from model.gast_net import SpatioTemporalModel, SpatioTemporalModelOptimized1f
     from common.skeleton import Skeleton
     from common.graph_utils import adj_mx_from_skeleton
-    adj = adj_mx_from_skeleton(Skeleton(synth.skeleton_parents(J), [], []))
-    m = SpatioTemporalModel(adj, J, 2, J, FW, causal=False, dropout=0.05, channels=CH)
+    adj = adj_mx_from_skeleton(Skeleton(synth.skeleton_parents(J_), [], []))
+    kls = SpatioTemporalModel if cls == 'full' else SpatioTemporalModelOptimized1f
+    m = kls(adj, J_, 2, J_, fw, causal=False, dropout=dropout, channels=ch)
     synth.randomize_module(m, 1)
     return m.to(device).eval()
+
+
+def kernel_share(prof):
+    """share of the fused GEMM family in the device time of one step, from the per-launch event pass.  The pass
+    brackets every launch with its own event pair, which adds a few microseconds per launch and removes the
+    overlap between a kernel's tail and the next one's head, so its SUM is not the step time; the SHARES are what
+    it measures (the ncu launch list under profiles/ is the cross-check)."""
+    tot = sum(prof['per_kernel_ms'].values())
+    return prof['gemm_ms_per_step'] / tot if tot > 0 else 0.0
+
+
+def roofline_of(prof, ms_per_step, flop_per_clip, clips, peaks, peak_src, traffic):
+    share = kernel_share(prof)
+    k_ms = share * ms_per_step                  # never exceeds the step it is part of
+    assert k_ms <= ms_per_step * (1 + 1e-9)
+    achieved = flop_per_clip * clips / (k_ms / 1000.0) / 1e12
+    peak_tf = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])
+    return {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
+            'frac_whole_step': flop_per_clip * clips / (ms_per_step / 1000.0) / 1e12 / peak_tf,
+            'traffic': traffic,
+            'kernel': 'fused GEMM family (%d launches/step)' % prof['gemm_launches'],
+            'kernel_ms_per_step': k_ms, 'kernel_share_of_step': share,
+            'peak_source': 'bf16_tflops_sustained of %s MEASURED_PEAKS (cuBLAS bf16, long loop)' % peak_src,
+            'per_kernel_ms_event_pass': {k: round(v, 4) for k, v in prof['per_kernel_ms'].items()}}
+
+
+def traffic_record():
+    """DRAM bytes of the GEMM-family launches of one step, from an `ncu --set full` capture (tools/ncu_summary.py
+    -> profiles/traffic.json).  The capture names the kernel-source hash it was taken from; a capture of another
+    build is reported as stale instead of being passed off as a measurement of this binary."""
+    tp = os.path.join(REPO, 'profiles', 'traffic.json')
+    if not os.path.exists(tp):
+        return None, 'no capture'
+    with open(tp) as f:
+        d = json.load(f)
+    cur = source_hash()
+    if d.get('source_hash') and d['source_hash'] != cur:
+        return d.get('dram_bytes_per_step'), 'STALE: captured from kernel sources %s, this build is %s' % (d['source_hash'], cur)
+    return d.get('dram_bytes_per_step'), d.get('source', '')
+
+
+def source_hash():
+    import hashlib
+    hsh = hashlib.sha1()
+    cs = os.path.join(PKG, 'csrc')
+    for fn in sorted(os.listdir(cs)):
+        if fn.endswith(('.cu', '.cuh')):
+            with open(os.path.join(cs, fn), 'rb') as f:
+                hsh.update(f.read())
+    return hsh.hexdigest()[:12]
+
+
+def time_forward(model, xs, K, W, barrier, stream):
+    import torch
+    with torch.no_grad():
+        for i in range(W):
+            model(xs[i % len(xs)])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(K):
+            model(xs[i % len(xs)])
+        e1.record(stream)
+        barrier()
+    return e0.elapsed_time(e1)
+
+
+def bench_other(name, cfg, device, rank, world, K, W, barrier, stream, reduce_max, peaks, peak_src):
+    """clips/s + roofline of one of the other BASELINE configurations on this rank's shard"""
+    import torch
+    from gast_b200 import synth, engine
+    m = build_model(device, cfg['J'], cfg['fw'], cfg['ch'])
+    per = cfg['global_clips'] // world
+    nbuf = 4
+    xs = [torch.from_numpy(synth.synth_input(per, cfg['T'], cfg['J'], 2, seed=77 + rank * 10 + i)).to(device)
+          for i in range(nbuf)]
+    ms = reduce_max(time_forward(m, xs, K, W, barrier, stream))
+    with torch.no_grad():
+        prof = engine.profile_forward(m, xs[0], reps=3)
+    launches = int(m._gast_last_launches)
+    del m, xs
+    torch.cuda.empty_cache()
+    rl = roofline_of(prof, ms / K, cfg['flop'], per, peaks, peak_src, None)
+    rl.pop('per_kernel_ms_event_pass')
+    return {'workload': cfg['what'], 'clips_per_gpu': per, 'global_clips': per * world, 'scaling': 'strong',
+            'value': per * world * K / (ms / 1000.0), 'unit': UNIT, 'ms_per_step': ms / K, 'gpu_launches_per_step': launches,
+            'gemm_core': prof['gemm_core'], 'roofline': rl}
+
+
+def bench_train(device, rank, world, K, W, barrier, stream, reduce_max, peaks):
+    """BASELINE configs[2]: `trainval.py -arc 3,3,3 -b 128` -- main.train()'s step (main.py:219-239) on
+    SpatioTemporalModelOptimized1f, b = 128 clips PER RANK (BatchNorm statistics per rank, like the replicas of
+    the reference's nn.DataParallel), dropout 0.05 (the reference default), one all-reduce of the flat gradient
+    buffer over NCCL when world > 1, Adam(amsgrad)."""
+    import torch
+    import torch.distributed as dist
+    from gast_b200 import synth
+    from gast_b200.trainer import DataParallelTrainer
+    from gast_b200.pipeline import FusedAdam
+    b = 128
+    m = build_model(device, J, FW, CH, cls='1f', dropout=0.05)
+    tr = DataParallelTrainer(m, lambda ps: FusedAdam(ps, lr=1e-3, amsgrad=True))
+    xs = [torch.from_numpy(synth.synth_input(b, T, J, 2, seed=300 + rank * 10 + i)).to(device) for i in range(4)]
+    ys = [torch.from_numpy(synth.synth_target(b, J, seed=400 + rank * 10 + i)).to(device) for i in range(4)]
+    for i in range(W):
+        loss = tr.step(xs[i % 4], ys[i % 4])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(K):
+        loss = tr.step(xs[i % 4], ys[i % 4])
+    e1.record(stream)
+    barrier()
+    ms = reduce_max(e0.elapsed_time(e1))
+    ar_ms = None
+    if world > 1:
+        for _ in range(3):
+            dist.all_reduce(tr.flat.flat)
+        barrier()
+        e0.record(stream)
+        for _ in range(20):
+            dist.all_reduce(tr.flat.flat)
+        e1.record(stream)
+        barrier()
+        ar_ms = reduce_max(e0.elapsed_time(e1)) / 20
+    fl = float(loss)
+    nparam = int(tr.flat.flat.numel())
+    peak_tf = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])
+    out = {'workload': 'BASELINE configs[2]: Optimized1f [3,3,3]/128ch train step (fwd + mpjpe + bwd + grad all-reduce '
+                       '+ Adam amsgrad), b=128 per rank, dropout 0.05',
+           'clips_per_gpu': b, 'global_clips': b * world, 'scaling': 'weak', 'ms_per_step': ms / K,
+           'value': b * world * K / (ms / 1000.0), 'unit': 'clips/s (training)',
+           'allreduce_ms': ar_ms, 'allreduce_bytes': 4 * nparam, 'last_loss': fl,
+           'frac_whole_step': TRAIN_FLOP_PER_CLIP * b / (ms / K / 1000.0) / 1e12 / peak_tf,
+           'gpu_launches_per_step_gemm': int(m._gast_last_launches)}
+    del tr, m
+    torch.cuda.empty_cache()
+    return out
 
 
 _CPU_STATE = {}
@@ -168,7 +318,9 @@ def run_reference(args, rank, world):
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': '27f/17j/128ch SpatioTemporalModel forward, eval, fp32 (BASELINE configs[1])',
                    'clips_per_step': sample, 'frames': T, 'joints': J, 'channels': CH,
-                   'impl': 'CPU port of the reference on the host cores'},
+                   'impl': 'CPU port of the reference on the host cores',
+                   'note': 'same model/metric as the GPU arm on a bounded sample: %d clips per step instead of 4096 '
+                           '(clips are independent; CPU throughput is flat in the batch size beyond ~64 clips)' % sample},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': '%d clips per step, needed-only (Optimized1f) schedule, torch-CPU port of the '
                                    'reference (oracle/gast_torch_ref.py, bit-identical to it)' % sample},
@@ -185,8 +337,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--clips', type=int, default=4096, help='clips per GPU per step')
-    ap.add_argument('--cpu-clips', type=int, default=64, help='clips per CPU-baseline sample')
+    ap.add_argument('--cpu-clips', type=int, default=256, help='clips per CPU-baseline sample / reference-arm step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-other-configs', action='store_true', help='headline (configs[1]) only')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -275,10 +428,31 @@ def main():
         from gast_b200 import engine
         prof = engine.profile_forward(model, xs_dev[0], reps=max(3, min(K, 10)))
 
-    t = torch.tensor([ms, ms_e2e, ms_e2e_serial], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_e2e_serial = float(t[0]), float(t[1]), float(t[2])
+    def reduce_max(v):
+        tt = torch.tensor([v], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt[0])
+
+    ms, ms_e2e, ms_e2e_serial = reduce_max(ms), reduce_max(ms_e2e), reduce_max(ms_e2e_serial)
+    peaks, peak_src = measured_peaks()
+
+    # ---------------- the other BASELINE configurations (after the headline region) -------------
+    other = {}
+    if not args.no_other_configs:
+        del xs_dev
+        model.__dict__.pop('_gast_handles', None)
+        torch.cuda.empty_cache()
+        Ko, Wo = max(5, min(K, 20)), 3
+        for name, cfg in OTHER.items():
+            try:
+                other[name] = bench_other(name, cfg, device, rank, world, Ko, Wo, barrier, stream, reduce_max, peaks, peak_src)
+            except Exception as e:                                   # a failing side config must not lose the headline
+                other[name] = {'error': repr(e)[:300]}
+        try:
+            other['cfg3_train_27f_17j_128ch_b128'] = bench_train(device, rank, world, Ko, Wo, barrier, stream, reduce_max, peaks)
+        except Exception as e:
+            other['cfg3_train_27f_17j_128ch_b128'] = {'error': repr(e)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -287,17 +461,21 @@ def main():
     total_clips = B * world * K
     value = total_clips / (ms / 1000.0)
     e2e_value = total_clips / (ms_e2e / 1000.0)
-    peaks, peak_src = measured_peaks()
-    # dominant kernel: the fused GEMM family (all launches of it in one step)
-    gemm_ms = prof['gemm_ms_per_step']
-    gemm_flops = FLOP_PER_CLIP * B      # >99% of the algorithmic FLOPs are the channel contractions
-    achieved_tf = gemm_flops / (gemm_ms / 1000.0) / 1e12
-    peak_tf = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])
-    traffic = None
-    tp = os.path.join(REPO, 'profiles', 'traffic.json')
-    if os.path.exists(tp):
-        with open(tp) as f:
-            traffic = json.load(f).get('dram_bytes_per_step')
+    # dominant kernel: the fused GEMM family (all launches of it in one step; >99% of the algorithmic FLOPs
+    # are the channel contractions)
+    traffic, traffic_src = traffic_record()
+    roof = roofline_of(prof, ms / K, FLOP_PER_CLIP, B, peaks, peak_src, traffic)
+    roof['traffic_source'] = traffic_src
+    roof['hbm_frac_compulsory'] = IO_BYTES_PER_CLIP * value / world / 1e9 / peaks['hbm_gbs']
+    from gast_b200 import _lib
+    ver = _lib.load().gast_version().decode()
+    # bf16-equivalent tensor passes per MAC: TF32 runs at half the bf16 rate, so 3xTF32 costs 6; one TF32 product
+    # + two bf16 correction products cost 2 + 2 = 4
+    div = 4 if 'bf16-corr' in ver else 6
+    roof['arithmetic'] = ver
+    roof['frac_of_fp32_parity_bound'] = roof['frac'] * div
+    roof['note'] = ('fp32-grade arithmetic (parity bar 1e-4 abs): every MAC costs %d bf16-equivalent tensor passes, so the '
+                    'attainable fraction of the bf16 peak is 1/%d' % (div, div))
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -314,16 +492,11 @@ def main():
                 'serial_value': total_clips / (ms_e2e_serial / 1000.0)},
         'gpu_launches': launches_per_step * K,
         'clocks': clocks,
-        'roofline': {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                     'frac': achieved_tf / peak_tf, 'frac_of_fp32_parity_bound': achieved_tf / (peak_tf / 6.0),
-                     'traffic': traffic,
-                     'kernel': 'fused GEMM family (%d launches/step)' % prof['gemm_launches'],
-                     'kernel_ms_per_step': gemm_ms, 'kernel_share_of_step': gemm_ms / prof['step_ms'],
-                     'peak_source': 'bf16_tflops_sustained of %s MEASURED_PEAKS; fp32-parity 3xTF32 bound is peak/6'
-                                    % peak_src,
-                     'hbm_frac_compulsory': IO_BYTES_PER_CLIP * value / world / 1e9 / peaks['hbm_gbs'],
-                     'per_kernel_ms': prof['per_kernel_ms']},
+        'roofline': roof,
+        'source_hash': source_hash(),
     }
+    if other:
+        line['other_configs'] = other
     if not args.no_cpu_baseline:
         v, cores, ts = cpu_port_clips_per_s(args.cpu_clips, 5)
         line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',

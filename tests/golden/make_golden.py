@@ -334,6 +334,34 @@ def tc_cases():
     model_case('tc_17_3333_c64_causal_full_T90', 17, [3, 3, 3, 3], 64, 1, 90, strided=False, causal=True)
 
 
+def stream_cases():
+    """N4 goldens (real-time causal path, gen_skes.py:43-69): what the reference produces for EVERY frame of a
+    sequence with a causal model -- its own UnchunkedGenerator(pad, causal_shift=pad) (common/generators.py:
+    210-221: pad + causal_shift edge-padded frames on the left, none on the right) feeding the causal dilated
+    SpatioTemporalModel, whose weights are interchangeable with the causal Optimized1f that the real-time
+    model is (gast_net.py:180-251).  A frame-by-frame streaming implementation must reproduce y[t] when frame t
+    is pushed."""
+    from common.generators import UnchunkedGenerator
+    for name, fw, ch, T, seed in (('stream_17_333_c32_causal', [3, 3, 3], 32, 45, 3),
+                                  ('stream_17_333_c128_causal', [3, 3, 3], 128, 33, 4),
+                                  ('stream_17_3333_c64_causal', [3, 3, 3, 3], 64, 100, 5)):
+        J = 17
+        m = SpatioTemporalModel(adj_for(J), J, 2, J, fw, causal=True, dropout=0.05, channels=ch)
+        synth.randomize_module(m, seed)
+        m.eval()
+        pad = (m.receptive_field() - 1) // 2
+        seqs = synth.synth_input(2, T, J, 2, 700 + seed)
+        ys = []
+        for sq in seqs:
+            gen = UnchunkedGenerator(None, None, [sq], pad=pad, causal_shift=pad, augment=False)
+            (_, _, b2), = list(gen.next_epoch())
+            assert b2.shape == (1, T + 2 * pad, J, 2)
+            ys.append(m(torch.from_numpy(b2.astype('float32'))).contiguous().numpy()[0])
+        meta = dict(kind='stream', J=J, filter_widths=fw, channels=ch, strided=False, causal=True, dense=False, seed=seed,
+                    keys=keys_shapes(m), receptive_field=m.receptive_field())
+        save(name, x=seqs, y=np.stack(ys), meta=meta)
+
+
 def main():
     torch.manual_seed(0)
     module_cases()
@@ -369,8 +397,11 @@ if __name__ == '__main__':
         train_cases()
     elif len(sys.argv) > 1 and sys.argv[1] == 'tc':
         tc_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'stream':
+        stream_cases()
     else:
         main()
         tta_cases()
         pipeline_cases()
         train_cases()
+        stream_cases()

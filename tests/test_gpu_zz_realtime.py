@@ -29,3 +29,27 @@ def test_causal_stream_equals_full_sequence_forward():
         want = mfull(torch.from_numpy(padded).cuda())
     assert want.shape == got.shape == (n, T, 17, 3)
     assert (got - want).abs().max().item() < TOL
+
+
+@pytest.mark.parametrize('name', ['stream_17_333_c32_causal', 'stream_17_333_c128_causal', 'stream_17_3333_c64_causal'])
+def test_causal_stream_vs_reference_golden(name):
+    """frame-by-frame output against what the UNMODIFIED reference produced for every frame of the sequence
+    (its UnchunkedGenerator(pad, causal_shift=pad) + causal model, tests/golden/make_golden.py:stream_cases)"""
+    from model.gast_net import SpatioTemporalModelOptimized1f
+    from test_gpu_parity import _adj
+    g = load_golden(name)
+    meta = g['meta']
+    m = SpatioTemporalModelOptimized1f(_adj(17), 17, 2, 17, meta['filter_widths'], causal=True, dropout=0.05,
+                                       channels=meta['channels'])
+    assert [[k, list(v.shape)] for k, v in m.state_dict().items()] == meta['keys']
+    synth.randomize_module(m, meta['seed'])
+    m = m.cuda().eval()
+    x, y = g['x'], g['y']                                         # (n, T, 17, 2), (n, T, 17, 3)
+    cs = CausalStream(m, n_streams=x.shape[0])
+    got = torch.stack([cs.push(torch.from_numpy(x[:, t]).cuda()) for t in range(x.shape[1])], dim=1).cpu().numpy()
+    err = float(np.abs(got - y).max())
+    assert err < TOL, err
+    # a stream that restarts: same outputs again
+    cs.reset()
+    again = torch.stack([cs.push(torch.from_numpy(x[:, t]).cuda()) for t in range(5)], dim=1).cpu().numpy()
+    assert np.abs(again - y[:, :5]).max() < TOL

@@ -101,7 +101,7 @@ def test_full_equals_1f_and_sliding_window():
 # ---------------------------------------------------------------------------------------------
 # the torch-CPU restatement (oracle/gast_torch_ref.py): same goldens, incl. the large ones
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('name', SMALL_MODELS + CFG_MODELS)
+@pytest.mark.parametrize('name', SMALL_MODELS + CFG_MODELS + golden_names('tc_'))
 def test_torch_ref_forward(name):
     import torch
     from oracle import gast_torch_ref as TR
