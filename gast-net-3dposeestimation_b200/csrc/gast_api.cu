@@ -43,7 +43,7 @@ static int fail(const char* fmt, ...) {
   } while (0)
 
 extern "C" const char* gast_last_error(void) { return g_err; }
-extern "C" const char* gast_version(void) { return "gast_b200 0.1 (sm_100a)"; }
+extern "C" const char* gast_version(void) { return "gast_b200 0.2 (sm_100a; tcgen05 tf32 + bf16-corr)"; }
 
 // ------------------------------------------------------------------------------------------
 // handle

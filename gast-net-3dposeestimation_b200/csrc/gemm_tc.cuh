@@ -1,16 +1,20 @@
-// tcgen05 (5th-gen tensor core) GEMM core of the lifting path: error-compensated 3xTF32.
+// tcgen05 (5th-gen tensor core) GEMM core of the lifting path: error-compensated TF32.
 //
-//   D[128 rows, 128 cols] (fp32, TMEM) += A_hi.B_hi + A_hi.B_lo + A_lo.B_hi      per 8-wide k-step
+//   D[128 rows, 128 cols] (fp32, TMEM) += A_hi.B_hi  (kind::tf32)  +  A_lo.B_hi + A_hi.B_lo  (kind::f16, bf16)
 //
-// where x_hi = tf32(x), x_lo = tf32(x - x_hi).  The dropped A_lo.B_lo term is 2^-22 relative,
-// so the result matches an fp32 FFMA GEMM to ~1e-6 (the parity bar is 1e-4 abs); a single
-// TF32 pass would not.  Same tiles, A-gather and fused epilogues as
-// gemm_ffma.cuh, so both cores are interchangeable per launch.
+// where x_hi = tf32(x), x_lo = x - x_hi.  The two correction products are 2^-11 of the result, so
+// they do not need TF32 operands: with bf16 operands (2^-9 relative operand error) they are good
+// to 2^-20 of the result, the same order as the dropped A_lo.B_lo term (2^-22) -- the result still
+// matches an fp32 FFMA GEMM to ~1e-6 (the parity bar is 1e-4 abs; a single TF32 pass would not,
+// SURVEY.md §7).  bf16 MMAs run at twice the TF32 rate, and both corrections together are ONE
+// K=64 bf16 product  [A_lo | A_hi] . [B_hi | B_lo]^T  per 32-wide K chunk, so a chunk costs
+// 4 (tf32) + 4 (bf16) tensor-pipe slots instead of the 12 of 3xTF32 (round 1).  Same tiles,
+// A-gather and fused epilogues as gemm_ffma.cuh, so both cores are interchangeable per launch.
 //
 // Persistent, warp-specialised CTA (one per SM, 2-CTA clusters share the B tile), 512 threads, registers
 // re-balanced with setmaxnreg (152 / 160 / 40 / 160):
-//   warps 0-3   A converters : raw A rows (TMA or cp.async ring in smem) -> hi/lo split -> tcgen05.st into
-//                              the A ring in TENSOR memory (TS-form MMA)
+//   warps 0-3   A converters : raw A rows (TMA or cp.async ring in smem) -> hi (tf32) | packed bf16 [lo | hi] ->
+//                              tcgen05.st into the A ring in TENSOR memory (TS-form MMA)
 //   warp  8     B producer   : TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B, cluster multicast) of the pre-split weights
 //   warp  9     MMA issuer   : one elected thread issues tcgen05.mma.kind::tf32, accumulators in TMEM
 //   warp  10    A producer   : TMA (cp.async.bulk.tensor.3d) of the raw A tile when the frame map is affine
@@ -28,6 +32,7 @@
 // a third TMEM buffer that is added once per tile.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <string.h>
 #include <vector>
 #include "gast_common.cuh"
@@ -35,8 +40,8 @@
 namespace gast {
 
 struct TcWeights {
-  float* hi = nullptr;
-  float* lo = nullptr;
+  float* hi = nullptr;   // [N][K] tf32-rounded weights
+  float* lo = nullptr;   // the same bytes as [N][2K] bf16: per 32-wide K chunk [hi | lo] (correction operand)
   CUtensorMap map_hi, map_lo;
   int N = 0, K = 0;
   bool ready = false;
@@ -188,6 +193,21 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
       "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+// D[tmem] (+)= A[tmem, bf16 pairs packed per 32-bit column] . B[smem desc, bf16]^T, kind::f16, K = 16 per instruction
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// two fp32 -> one 32-bit register of two bf16 (round to nearest even): `lo_k` in bits 0-15 (the lower k index)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_k, float hi_k) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_k), "f"(lo_k));
+  return d;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -279,7 +299,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // Tensor-memory map (512 columns x 128 lanes x 32 bit):
 //   [0,256)   main accumulator ring (2 x 128): A_hi.B_hi of ONE 32-wide K chunk
 //   [256,384) correction accumulator: A_lo.B_hi + A_hi.B_lo over the whole K
-//   [384,512) A operand ring (2 stages x {hi 32 cols, lo 32 cols}): row m in lane m, k in columns
+//   [384,512) A operand ring (2 stages x {hi: 32 tf32 columns | 16 columns of bf16 pairs of lo | 16 of hi}):
+//             row m in lane m, k along the columns
 constexpr uint32_t TC_NMAIN = 2;
 constexpr uint32_t TC_CORR_COL = 256;
 constexpr uint32_t TC_A_COL = 384;
@@ -287,6 +308,9 @@ constexpr uint32_t TC_A_COL = 384;
 // instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=128
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
                               ((uint32_t)(TC_BM >> 4) << 24);
+// the same with A=B=bf16 (kind::f16 format code 1), for the correction products
+constexpr uint32_t TC_IDESC_BF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                                 ((uint32_t)(TC_BM >> 4) << 24);
 
 // ----------------------------------------------------------------------------------------
 // kernel
@@ -460,9 +484,9 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       }
       if (DBG == 6) { long long tq1 = clock64(); tA_ld += tq1 - tq0; tq0 = tq1; }
       uint32_t hi[32], lo[32];
-      // hi = RN to tf32 (11 significant bits); lo = x - hi exactly.  lo is handed over
-      // unrounded: the tensor core truncates it to tf32, an error <= 2^-21 |x| whose sign
-      // is that of -lo, i.e. unbiased because hi was rounded to nearest.
+      // hi = RN to tf32 (11 significant bits); lo = x - hi exactly.  The correction operand is the
+      // K = 64 bf16 row [lo(k = 0..31) | hi(k = 0..31)], two values per 32-bit column (lower k in the
+      // low half): lo[0..15] = pairs of x_lo, lo[16..31] = pairs of x_hi, both rounded to nearest.
       const float* rowp = atma
           ? reinterpret_cast<const float*>(smem + TC_OFF_XPOSE + slot * 16384 + my_row * 128)
           : reinterpret_cast<const float*>(smem + TC_OFF_XPOSE) + (size_t)slot * 128 * TC_XLD + (size_t)my_row * TC_XLD;
@@ -471,11 +495,13 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       for (int i = 0; i < 8; ++i) {
         float4 x = *reinterpret_cast<const float4*>(rowp + ((i ^ sw) << 2));
         if (atma && !row_in_box) x = make_float4(0.f, 0.f, 0.f, 0.f);   // rows the box does not cover
-        float h;
-        h = tf32_rn_fast(x.x); hi[4 * i + 0] = __float_as_uint(h); lo[4 * i + 0] = __float_as_uint(x.x - h);
-        h = tf32_rn_fast(x.y); hi[4 * i + 1] = __float_as_uint(h); lo[4 * i + 1] = __float_as_uint(x.y - h);
-        h = tf32_rn_fast(x.z); hi[4 * i + 2] = __float_as_uint(h); lo[4 * i + 2] = __float_as_uint(x.z - h);
-        h = tf32_rn_fast(x.w); hi[4 * i + 3] = __float_as_uint(h); lo[4 * i + 3] = __float_as_uint(x.w - h);
+        const float h0 = tf32_rn_fast(x.x), h1 = tf32_rn_fast(x.y), h2 = tf32_rn_fast(x.z), h3 = tf32_rn_fast(x.w);
+        hi[4 * i + 0] = __float_as_uint(h0); hi[4 * i + 1] = __float_as_uint(h1);
+        hi[4 * i + 2] = __float_as_uint(h2); hi[4 * i + 3] = __float_as_uint(h3);
+        lo[2 * i + 0] = pack_bf16x2(x.x - h0, x.y - h1);
+        lo[2 * i + 1] = pack_bf16x2(x.z - h2, x.w - h3);
+        lo[16 + 2 * i + 0] = pack_bf16x2(h0, h1);
+        lo[16 + 2 * i + 1] = pack_bf16x2(h2, h3);
       }
       __syncwarp();                         // slot free
       if (DBG == 6) { long long tq1 = clock64(); tA_x += tq1 - tq0; tq0 = tq1; }
@@ -536,11 +562,11 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
             const uint32_t dst = sbase + stage * TC_STAGE_BYTES + crank * (R * 128);
             const uint16_t mask = (uint16_t)((1u << TC_CLUSTER) - 1);
             tma_load_2d_mc(dst, &map_hi, full, c * TC_BK, n0 + R * (int)crank, mask);
-            tma_load_2d_mc(dst + 16384, &map_lo, full, c * TC_BK, n0 + R * (int)crank, mask);
+            tma_load_2d_mc(dst + 16384, &map_lo, full, c * 2 * TC_BK, n0 + R * (int)crank, mask);   // bf16 [hi | lo] row of this chunk
           } else {
             const uint32_t dst = sbase + stage * TC_STAGE_BYTES;
             tma_load_2d(dst, &map_hi, full, c * TC_BK, n0);
-            tma_load_2d(dst + 16384, &map_lo, full, c * TC_BK, n0);
+            tma_load_2d(dst + 16384, &map_lo, full, c * 2 * TC_BK, n0);
           }
           if (++stage == TC_BSTAGES) { stage = 0; phase ^= 1; }
         }
@@ -608,9 +634,9 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           if (DBG == 6) t3 = clock64();
           tc_fence_after();
           const uint32_t d_main = tmem_base + mb * TC_BN;
-          const uint32_t a_hi = tmem_base + TC_A_COL + as * 64, a_lo = a_hi + 32;
+          const uint32_t a_hi = tmem_base + TC_A_COL + as * 64, a_pk = a_hi + 32;
           const uint32_t sb = sbase + bs * TC_STAGE_BYTES;
-          const uint64_t b_hi = make_smem_desc(sb), b_lo = make_smem_desc(sb + 16384);
+          const uint64_t b_hi = make_smem_desc(sb), b_pk = make_smem_desc(sb + 16384);
           const bool last_of_group = (cg == TC_FLUSH - 1 || c == nchunks - 1);
           // ring positions of the next chunk (same rings across tile boundaries)
           const int as_n = (as + 1 == TC_ASTAGES) ? 0 : as + 1, bs_n = (bs + 1 == TC_BSTAGES) ? 0 : bs + 1;
@@ -621,10 +647,9 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
             if (elect_one()) {
               const uint64_t adv = (uint64_t)(k * 2);      // 8 fp32 = 32 B = 2 x 16 B
               umma_tf32_ts(d_main, a_hi + 8 * k, b_hi + adv, TC_IDESC, (cg | k) ? 1u : 0u);
-              if (DBG != 3) {
-                umma_tf32_ts(d_corr, a_lo + 8 * k, b_hi + adv, TC_IDESC, (c | k) ? 1u : 0u);
-                umma_tf32_ts(d_corr, a_hi + 8 * k, b_lo + adv, TC_IDESC, 1u);
-              }
+              // correction: bf16 k-step k of the K=64 row [A_lo | A_hi] . [B_hi | B_lo]^T (8 columns of bf16
+              // pairs in tensor memory, 32 bytes of the swizzled B row, like a tf32 k-step)
+              if (DBG != 3) umma_bf16_ts(d_corr, a_pk + 8 * k, b_pk + adv, TC_IDESC_BF, (c | k) ? 1u : 0u);
               if (k == TC_BK / 8 - 1) {
                 if (TC_CLUSTER > 1) umma_commit_mc(bar0 + BB_EMPTY + 8 * bs, (uint16_t)((1u << TC_CLUSTER) - 1));
                 else umma_commit(bar0 + BB_EMPTY + 8 * bs);     // frees the B smem stage when the MMAs retire
@@ -1079,27 +1104,32 @@ constexpr float TC_TRUNC_C = 3.5e-8f;
 // semch != 0: W is the SemCH packing of gast_api.cu ([W0 of 64 channels | W1 of the same 64] per
 // 128-row tile); the copies interleave it per 32 channels ([W0 32 | W1 32 | W0 next 32 | W1 next 32]) so
 // that each epilogue warpgroup (64 accumulator columns) holds self and neighbour terms of the same channels.
-__global__ void tc_split_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo,
+// `pk` is the bf16 operand of the correction product: row n, chunk c (32 k's) holds
+// [hi(k = 32c .. 32c+31) | lo(k = 32c .. 32c+31)] as 64 bf16 = one 128-byte swizzle row of the B stage.
+__global__ void tc_split_kernel(const float* __restrict__ w, float* __restrict__ hi, unsigned short* __restrict__ pk,
                                 long long n, int K, int semch) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   long long src = i;
+  const long long row = i / K;
   if (semch) {
-    const long long row = i / K;
     const int within = (int)(row & 127), half = within >> 6, sub = within & 63;
     const int srow = (sub >> 5) * 64 + half * 32 + (sub & 31);
     src = ((row & ~127LL) + srow) * K + (i - row * K);
   }
   float x = w[src];
   float h = tf32_rna(x);
-  const int k = (int)(i % K);
+  const int k = (int)(i - row * K);
   const int nchunks = K / TC_BK;
   const int c = k / TC_BK, g = c / TC_FLUSH;
   const int glen = min(TC_FLUSH, nchunks - g * TC_FLUSH);            // chunks in this flush group
   const int s = (c - g * TC_FLUSH) * (TC_BK / 8) + (k % TC_BK) / 8;  // k-step index inside the group
   const float steps_left = (float)(glen * (TC_BK / 8) - s);          // truncations this product still sees
   hi[i] = h;
-  lo[i] = tf32_rna((x - h) + TC_TRUNC_C * steps_left * h);
+  const float lo = (x - h) + TC_TRUNC_C * steps_left * h;
+  unsigned short* prow = pk + row * 2 * K + (long long)c * 2 * TC_BK + (k - c * TC_BK);
+  prow[0] = __bfloat16_as_ushort(__float2bfloat16_rn(h));
+  prow[TC_BK] = __bfloat16_as_ushort(__float2bfloat16_rn(lo));
 }
 
 typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1141,14 +1171,17 @@ inline int tc_prepare_weights(TcWeights& t, const float* W, int N, int K, cudaSt
     CUresult r1 = enc(&t.map_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, t.hi, dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    CUresult r2 = enc(&t.map_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, t.lo, dims, strides, box, estr,
+    // the bf16 [hi | lo] rows: [N][2K] bf16 (the same bytes per row as the fp32 matrix), 64 elements = 128 B per box row
+    cuuint64_t dims_b[2] = {(cuuint64_t)2 * K, (cuuint64_t)N};
+    cuuint32_t box_b[2] = {(cuuint32_t)(2 * TC_BK), (cuuint32_t)(TC_BN / TC_CLUSTER)};
+    CUresult r2 = enc(&t.map_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, t.lo, dims_b, strides, box_b, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return -1;
   }
   long long n = (long long)N * K;
   if (semch && N % 128) return -1;
-  tc_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, t.hi, t.lo, n, K, semch);
+  tc_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, t.hi, reinterpret_cast<unsigned short*>(t.lo), n, K, semch);
   t.ready = true;
   return 0;
 }

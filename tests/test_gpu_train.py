@@ -211,32 +211,37 @@ def test_training_vs_reference_fixture(name):
     m = TF.build_module(meta).cuda().train()
     opt = torch.optim.Adam(m.parameters(), lr=meta['lr'], amsgrad=meta['amsgrad'])
     rep = ['== ' + name]
+    bad = []
     for step in range(meta['nsteps']):
         x, tgt = TF.batch(meta, step)
         opt.zero_grad()
         y = m(x.cuda())
         loss = torch.mean(torch.norm(y - tgt.cuda(), dim=3))
         loss.backward()
-        TF.check_step(g, step, y.detach().cpu().numpy(), loss.item(), {k: p.grad for k, p in m.named_parameters()},
-                      y_tol=5e-5, loss_rtol=1e-5, ent_rtol=3e-2, norm_rtol=3e-2, report=rep)
+        bad += TF.check_step(g, step, y.detach().cpu().numpy(), loss.item(), {k: p.grad for k, p in m.named_parameters()},
+                             y_tol=5e-5, loss_rtol=1e-5, ent_rtol=3e-2, norm_rtol=3e-2, report=rep)
         opt.step()
     sd = m.state_dict()
     worst = 0.0
+    gmax = max(float(g['gsum0/' + k][0]) for k in meta['names'])
     for k in meta['names']:
-        if float(g['gsum0/' + k][0]) < 1e-12:
-            continue                                      # zero-gradient parameter: Adam moves it by noise
+        if float(g['gsum0/' + k][0]) < 1e-5 * gmax:
+            continue                                      # noise-level gradient: Adam moves the parameter by +-lr at random
         _, ent = TF.digest(sd[k], g['idx/' + k])
         d = float(np.abs(ent - g['pent/' + k]).max())
         worst = max(worst, d)
-        assert d < 2e-5, (k, d)                           # parameters after the Adam steps, at the large-|g| entries
+        if not d < 2e-5:                                  # parameters after the Adam steps, at the large-|g| entries
+            bad.append(('parameter after the steps', k, d))
     for k in sd:
         if 'running_' in k:
             ref = g['stat/' + k]
-            assert np.abs(sd[k].cpu().numpy() - ref).max() < 1e-4 * max(1.0, np.abs(ref).max()), k
+            if not np.abs(sd[k].cpu().numpy() - ref).max() < 1e-4 * max(1.0, np.abs(ref).max()):
+                bad.append(('running statistic', k))
         if 'num_batches' in k:
             assert int(sd[k]) == int(g['stat/' + k])
     rep.append('post-step parameters: max |delta| at the fingerprint entries %.3g' % worst)
     _report('train_fixture_report.txt', rep)
+    assert not bad, bad[:10]
 
 
 def test_two_forwards_before_backward_and_no_grad_forward():

@@ -41,30 +41,41 @@ def digest(t, idx):
 def check_step(g, step, y, loss, grads, y_tol, loss_rtol, ent_rtol, norm_rtol, report=None):
     """compare one step of an implementation with the fixture.  grads: name -> tensor.
     ent_rtol: tolerance on the stored large-|g| entries relative to the largest of them;
-    norm_rtol: tolerance on ||g||."""
+    norm_rtol: tolerance on ||g||.  Every violation is collected (and reported) before the assert."""
+    bad = []
     yr = g['y%d' % step]
     scale = max(1.0, float(np.abs(yr).max()))
     ey = float(np.abs(y - yr).max())
-    assert ey < y_tol * scale, ('y', step, ey)
+    if not ey < y_tol * scale:
+        bad.append(('y', step, ey))
     lr = float(g['loss%d' % step])
     el = abs(loss - lr) / abs(lr)
-    assert el < loss_rtol, ('loss', step, loss, lr)
+    if not el < loss_rtol:
+        bad.append(('loss', step, loss, lr))
+    # gradients that are zero by construction (init_bn.bias: expand_bn removes any constant it adds) are pure
+    # rounding noise in ANY implementation, the reference included: they only have to stay noise-sized
+    gmax = max(float(g['gsum%d/%s' % (step, k)][0]) for k in g['meta']['names'])
     worst = (0.0, None)
     for k in g['meta']['names']:
         ns_ref, ent_ref = g['gsum%d/%s' % (step, k)], g['gent%d/%s' % (step, k)]
         ns, ent = digest(grads[k], g['idx/' + k])
-        if ns_ref[0] < 1e-12:                     # identically zero gradient (init_bn.bias): rounding noise only
-            assert ns[0] < 1e-5, (k, ns[0])
+        if ns_ref[0] < 1e-5 * gmax:
+            if not ns[0] < 1e-4 * gmax:
+                bad.append(('noise-level gradient grew', step, k, ns[0]))
             continue
         en = abs(ns[0] - ns_ref[0]) / ns_ref[0]
         ee = float(np.abs(ent - ent_ref).max() / np.abs(ent_ref).max())
         if max(en, ee) > worst[0]:
             worst = (max(en, ee), k)
-        assert en < norm_rtol, ('grad norm', step, k, ns[0], ns_ref[0])
-        assert ee < ent_rtol, ('grad entries', step, k, ee)
+        if not en < norm_rtol:
+            bad.append(('grad norm', step, k, ns[0], ns_ref[0]))
+        if not ee < ent_rtol:
+            bad.append(('grad entries', step, k, ee))
     if report is not None:
-        report.append(('step %d: max|dy| %.3g  loss rel %.3g  worst grad fingerprint %.3g (%s)'
-                       % (step, ey, el, worst[0], worst[1])))
+        report.append(('step %d: max|dy| %.3g  loss rel %.3g  worst grad fingerprint %.3g (%s)  violations %d'
+                       % (step, ey, el, worst[0], worst[1], len(bad))))
+        report.extend('   ' + repr(b) for b in bad[:20])
+    return bad
 
 
 __all__ = ['load_golden', 'build_module', 'batch', 'digest', 'check_step', 'adj_t']

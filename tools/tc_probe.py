@@ -42,7 +42,7 @@ def perf():
         a = torch.from_numpy(rs.standard_normal((M, K)).astype(np.float32)).cuda()
         w = torch.from_numpy(rs.standard_normal((N, K)).astype(np.float32)).cuda()
         o = torch.empty((M, N), dtype=torch.float32, device='cuda')
-        mma_bound = 3.0 * (-(-M // 128) * 128) * (-(-N // 128) * 128) * K / (2048.0 * 148 * 1.9e9) * 1e3
+        mma_bound = (2.0 if b"bf16-corr" in lib.gast_version() else 3.0) * (-(-M // 128) * 128) * (-(-N // 128) * 128) * K / (2048.0 * 148 * 1.9e9) * 1e3
         line = 'M=%d N=%d K=%d  MMA-bound %.3f ms |' % (M, N, K, mma_bound)
         for core, mode, name in ((1, 0, 'ffma'), (0, 0, 'tc'), (0, 1, 'noflush'), (0, 2, 'noAload'), (0, 3, 'mainonly'),
                                  (0, 4, 'noSTTM'), (0, 5, 'mma+B only')):
