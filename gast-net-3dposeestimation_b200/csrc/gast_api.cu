@@ -70,6 +70,8 @@ struct StageConsts {
   int Cw = 0, taps = 0, stride = 1, dil = 1;
   float *Wt = nullptr, *bt = nullptr, *W1 = nullptr, *b1 = nullptr;
   TcWeights tc_t, tc_1;
+  std::vector<float*> Wrot;          // streaming (stream.cuh): tap-rotated copies of Wt, one per rotation
+  std::vector<TcWeights> tc_rot;
 };
 
 struct gast_handle {
@@ -89,6 +91,7 @@ struct gast_handle {
   std::vector<int> pad, shift;       // gast_net.py:57,136-143
   float *We = nullptr, *be = nullptr;
   bool prepared = false;
+  bool stream_ready = false;         // tap-rotated stage weights match the current parameters
   int launches = 0;
   int tc_launches = 0;
   int gemm_core = 0;                 // 0 auto (tcgen05 where possible), 1 force FFMA
@@ -449,6 +452,7 @@ extern "C" int gast_prepare(gast_t* h, void* stream) {
   if (prepare_tc(h, st)) return 1;
   CUDA_OK(cudaGetLastError());
   h->prepared = true;
+  h->stream_ready = false;
   return 0;
 }
 
@@ -847,10 +851,13 @@ extern "C" int gast_forward(gast_t* h, const float* x, float* y, int32_t B, int3
   return 0;
 }
 
+static int prep_one_tc(gast_handle* h, cudaStream_t st, TcWeights& t, const float* W, int N, int K, int semch);
+#include "stream.cuh"
+
 // ------------------------------------------------------------------------------------------
 // tcgen05 weight copies
 // ------------------------------------------------------------------------------------------
-static int prep_one_tc(gast_handle* h, cudaStream_t st, TcWeights& t, const float* W, int N, int K, int semch = 0) {
+static int prep_one_tc(gast_handle* h, cudaStream_t st, TcWeights& t, const float* W, int N, int K, int semch) {
   if (!W) return 0;
   int rc = tc_prepare_weights(t, W, N, K, st, &h->owned, semch);
   if (rc) return fail("tcgen05 weight preparation failed (%d): %s", rc,
@@ -864,14 +871,14 @@ static int prepare_tc(gast_handle* h, cudaStream_t st) {
     const int C = b.C;
     const int nmask = (kind == GAST_KIND_SEMCH) ? 1 : 2;
     if (prep_one_tc(h, st, b.tc_loc, b.Wloc, nmask * b.tpm * 128, C, 1)) return 1;
-    if (prep_one_tc(h, st, b.tc_lc, b.Wlc, C, 2 * C)) return 1;
-    if (prep_one_tc(h, st, b.tc_g, b.Wg, b.heads * b.Cg, C)) return 1;
-    if (prep_one_tc(h, st, b.tc_gc, b.Wgc, C, C)) return 1;
-    if (prep_one_tc(h, st, b.tc_bc, b.Wbc, 2 * C, 3 * C)) return 1;
+    if (prep_one_tc(h, st, b.tc_lc, b.Wlc, C, 2 * C, 0)) return 1;
+    if (prep_one_tc(h, st, b.tc_g, b.Wg, b.heads * b.Cg, C, 0)) return 1;
+    if (prep_one_tc(h, st, b.tc_gc, b.Wgc, C, C, 0)) return 1;
+    if (prep_one_tc(h, st, b.tc_bc, b.Wbc, 2 * C, 3 * C, 0)) return 1;
   }
   for (StageConsts& s : h->stages) {
-    if (prep_one_tc(h, st, s.tc_t, s.Wt, s.Cw, s.taps * s.Cw)) return 1;
-    if (prep_one_tc(h, st, s.tc_1, s.W1, s.Cw, s.Cw)) return 1;
+    if (prep_one_tc(h, st, s.tc_t, s.Wt, s.Cw, s.taps * s.Cw, 0)) return 1;
+    if (prep_one_tc(h, st, s.tc_1, s.W1, s.Cw, s.Cw, 0)) return 1;
   }
   return 0;
 }

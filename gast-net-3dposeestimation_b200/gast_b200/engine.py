@@ -284,10 +284,8 @@ def _no_train(module, what):
 
 
 # ------------------------------------------------------------------------------------------
-def run_model(module, x):
-    """SpatioTemporalModelBase.forward (gast_net.py:84-104) on the CUDA library."""
-    _require_cuda(x, 'SpatioTemporalModel.forward')
-    dev = x.device
+def model_handle(module, dev):
+    """the C handle of a SpatioTemporalModel / ...Optimized1f instance on `dev` (created on first use)"""
     blk0 = module.layers_graph_conv[0].local_graph_layer
 
     def make():
@@ -296,7 +294,14 @@ def run_model(module, x):
             channels=module._gast_channels, filter_widths=list(module.filter_widths),
             causal=module._gast_causal, dense=module._gast_dense, strided=module._gast_strided, heads=4),
             sym=blk0.gcn_sym.m, con=blk0.gcn_con.m)
-    h = _handle_for(module, dev, make)
+    return _handle_for(module, dev, make)
+
+
+def run_model(module, x):
+    """SpatioTemporalModelBase.forward (gast_net.py:84-104) on the CUDA library."""
+    _require_cuda(x, 'SpatioTemporalModel.forward')
+    dev = x.device
+    h = model_handle(module, dev)
     x = x.contiguous()
     B, T = int(x.shape[0]), int(x.shape[1])
     if module.training:

@@ -142,6 +142,22 @@ int gast_forward_train(gast_t* h, const float* x, float* y, int32_t B, int32_t T
                        void* workspace, size_t workspace_bytes, void* stream);
 int gast_backward(gast_t* h, const float* dy, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- real-time causal streams (gen_skes.py:43-69, tools/inference.py:19-110) -------------
+ * The reference's real-time model is a causal SpatioTemporalModelOptimized1f re-run on the last
+ * receptive_field frames for every new frame.  Here a pushed frame costs ONE new position per layer: `state`
+ * (caller-owned device memory, gast_stream_state_bytes, contents irrelevant before the first push) holds per
+ * temporal stage a ring of that stage's past inputs for n_streams concurrent streams.
+ * gast_stream_push: x (n_streams, J, in_features) = the newest frame of every stream -> y (n_streams, J, 3) =
+ *   its 3D pose, identical to the whole-sequence causal forward on the sequence so far, left-padded by
+ *   replicating the stream's first frame (UnchunkedGenerator(pad, causal_shift=pad), common/generators.py:210-221).
+ *   step = number of frames pushed into `state` before this one (0, 1, 2, ...; the caller counts).
+ *   fresh (n_streams) int32 on the device, or null: non-zero = this frame starts a new sequence on that stream
+ *   (must be non-zero for every stream at step 0).  MODEL handles with causal = 1 only; all work on `stream`. */
+size_t gast_stream_state_bytes(gast_t* h, int32_t n_streams);
+size_t gast_stream_workspace_bytes(gast_t* h, int32_t n_streams);
+int gast_stream_push(gast_t* h, void* state, int64_t step, const float* x, float* y, int32_t n_streams,
+                     const int32_t* fresh, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- either side of the forward, on the device --------------------------------
  * All pointers are device pointers unless marked (host).  Work is enqueued on `stream`.
  *

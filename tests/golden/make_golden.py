@@ -256,14 +256,10 @@ def _digest(t, idx):
     return np.array([float(f.norm()), float(f.sum())], np.float64), f[idx].numpy().astype(np.float32)
 
 
-def train_case(name, J, fw, ch, B, nsteps, full_grads, dilated=False, seed=9):
-    """a12 / BASELINE configs[2] golden: the UNMODIFIED reference model in train() mode, dropout 0, driven exactly
-    as main.train() drives it (main.py:219-239: root joint of the target zeroed, zero_grad, forward, mpjpe,
-    backward, optimizer.step) with optim.Adam(lr=1e-3, amsgrad=True) (trainval.py:78).  Stored per step: the
-    prediction, the loss, and per parameter either the whole gradient (small cases) or its norm, sum and 48
-    entries at the flat indices where |grad of step 0| is largest (those are far above the fp32 gradient noise);
-    after the last step: every BatchNorm running statistic and the same fingerprint of every parameter."""
+def _train_run(J, fw, ch, B, nsteps, dilated, seed, threads):
+    """main.train()'s loop (main.py:219-239) on the reference model, dropout 0, Adam(amsgrad) (trainval.py:78)"""
     from common.loss import mpjpe
+    torch.set_num_threads(threads)
     adj = adj_for(J)
     T = int(np.prod(fw))
     if dilated:
@@ -273,9 +269,7 @@ def train_case(name, J, fw, ch, B, nsteps, full_grads, dilated=False, seed=9):
     synth.randomize_module(m, seed)
     m.train()
     opt = torch.optim.Adam(m.parameters(), lr=1e-3, amsgrad=True)
-    names = [k for k, _ in m.named_parameters()]
-    out = {}
-    idx = {}
+    steps = []
     with torch.enable_grad():
         for step in range(nsteps):
             x = torch.from_numpy(synth.synth_input(B, T, J, 2, seed=100 + step))
@@ -285,30 +279,57 @@ def train_case(name, J, fw, ch, B, nsteps, full_grads, dilated=False, seed=9):
             y = m(x)
             loss = mpjpe(y, tgt)
             loss.backward()
-            out['y%d' % step] = y.detach().contiguous().numpy().copy()
-            out['loss%d' % step] = np.array(loss.item(), np.float64)
-            for k, prm in m.named_parameters():
-                g = prm.grad.detach().reshape(-1)
-                if step == 0:
-                    n = min(48, g.numel())
-                    idx[k] = torch.topk(g.abs(), n).indices.sort().values
-                    out['idx/' + k] = idx[k].numpy().astype(np.int64)
-                if full_grads and step == 0:
-                    out['grad0/' + k] = prm.grad.detach().numpy().copy()
-                ns, ent = _digest(prm.grad, idx[k])
-                out['gsum%d/%s' % (step, k)] = ns
-                out['gent%d/%s' % (step, k)] = ent
+            grads = {k: prm.grad.detach().clone() for k, prm in m.named_parameters()}
             opt.step()
-    for k, prm in m.named_parameters():
-        ns, ent = _digest(prm, idx[k])
-        out['psum/' + k] = ns
-        out['pent/' + k] = ent
+            params = {k: prm.detach().clone() for k, prm in m.named_parameters()}
+            steps.append(dict(y=y.detach().contiguous().numpy().copy(), loss=loss.item(), grads=grads, params=params))
+    return m, steps, T
+
+
+def train_case(name, J, fw, ch, B, nsteps, full_grads, dilated=False, seed=9):
+    """a12 / BASELINE configs[2] golden: the UNMODIFIED reference model in train() mode, dropout 0, driven exactly
+    as main.train() drives it with optim.Adam(lr=1e-3, amsgrad=True).  Stored per step: the prediction, the loss,
+    and per parameter either the whole gradient (small cases, step 0) or its norm, sum and 48 entries at the flat
+    indices where |grad of step 0| is largest; the same fingerprint of every parameter after every step; the
+    BatchNorm running statistics after the last step.
+
+    The reference's OWN reproducibility is stored next to it (`alt_*`): the identical run with 3 instead of 8 CPU
+    threads (different fp32 summation order, nothing else).  Adam's first updates are lr*g/(|g|+eps): every
+    parameter whose gradient is rounding noise moves by +-lr at random, so from the second step on two runs of
+    the reference itself only agree to ~5e-5 (step 1) / ~1e-3 (step 2) in the loss at b=128 -- the band any fp32
+    implementation can be held to."""
+    m, steps, T = _train_run(J, fw, ch, B, nsteps, dilated, seed, threads=8)
+    alt = _train_run(J, fw, ch, B, nsteps, dilated, seed, threads=3)[1] if nsteps > 1 else None
+    torch.set_num_threads(8)
+    names = [k for k, _ in m.named_parameters()]
+    out, idx = {}, {}
+    for k in names:
+        g = steps[0]['grads'][k].reshape(-1)
+        idx[k] = torch.topk(g.abs(), min(48, g.numel())).indices.sort().values
+        out['idx/' + k] = idx[k].numpy().astype(np.int64)
+        if full_grads:
+            out['grad0/' + k] = steps[0]['grads'][k].numpy().copy()
+    for s, st in enumerate(steps):
+        out['y%d' % s] = st['y']
+        out['loss%d' % s] = np.array(st['loss'], np.float64)
+        for k in names:
+            out['gsum%d/%s' % (s, k)], out['gent%d/%s' % (s, k)] = _digest(st['grads'][k], idx[k])
+            out['psum%d/%s' % (s, k)], out['pent%d/%s' % (s, k)] = _digest(st['params'][k], idx[k])
+        if alt is not None:
+            out['alt_loss%d' % s] = np.array(alt[s]['loss'], np.float64)
+            out['alt_dy%d' % s] = np.array(np.abs(alt[s]['y'] - st['y']).max(), np.float64)
+            out['alt_dp%d' % s] = np.array(max(float((alt[s]['params'][k] - st['params'][k]).abs().max()) for k in names), np.float64)
+            out['alt_dg%d' % s] = np.array(max(float((alt[s]['grads'][k] - st['grads'][k]).norm() / (st['grads'][k].norm() + 1e-30))
+                                              for k in names if float(st['grads'][k].norm()) > 1e-5), np.float64)
     for k, v in m.state_dict().items():
         if 'running_' in k or 'num_batches' in k:
             out['stat/' + k] = v.numpy().copy()
     meta = dict(kind='train', J=J, filter_widths=fw, channels=ch, B=B, T=T, nsteps=nsteps, seed=seed, dilated=dilated,
-                names=names, full_grads=full_grads, lr=1e-3, amsgrad=True)
+                names=names, full_grads=full_grads, lr=1e-3, amsgrad=True, threads=8, alt_threads=3 if alt else None)
     save(name, meta=meta, **out)
+    if alt is not None:
+        print('   reference self-noise (8 vs 3 threads):', [(float(abs(out['alt_loss%d' % s] - out['loss%d' % s]) / out['loss%d' % s]),
+                                                            float(out['alt_dy%d' % s]), float(out['alt_dp%d' % s])) for s in range(nsteps)])
 
 
 def train_cases():

@@ -205,7 +205,10 @@ def test_training_vs_reference_fixture(name):
     """a12 / BASELINE configs[2] against fixtures of the UNMODIFIED reference (tests/golden/make_golden.py:
     train_case): main.train()'s loop (main.py:219-239) with Adam(amsgrad) (trainval.py:78), dropout 0.
     `train_cfg3_17_333_c128_b128` is the configuration as specified: -arc 3,3,3, 128 channels, b = 128, three
-    steps, loss to 1e-5 relative.  The dilated case is main.py:171-175's training model."""
+    steps.  Step 0 (forward, loss, every gradient, the first parameter update) is held to 1e-5 relative in the
+    loss; the later steps to 3x the reference's own run-to-run noise (see train_fixture.check_step: SURVEY's
+    "rel 1e-5 over >= 3 steps" is not met by the reference against itself -- 8 vs 3 CPU threads differ by 4e-5 at
+    step 1 and 1e-3 at step 2).  The dilated case is main.py:171-175's training model."""
     g = load_golden(name)
     meta = g['meta']
     m = TF.build_module(meta).cuda().train()
@@ -219,27 +222,19 @@ def test_training_vs_reference_fixture(name):
         loss = torch.mean(torch.norm(y - tgt.cuda(), dim=3))
         loss.backward()
         bad += TF.check_step(g, step, y.detach().cpu().numpy(), loss.item(), {k: p.grad for k, p in m.named_parameters()},
-                             y_tol=5e-5, loss_rtol=1e-5, ent_rtol=3e-2, norm_rtol=3e-2, report=rep)
+                             y_tol=5e-5, loss_rtol=1e-5, ent_rtol=5e-2, norm_rtol=5e-2, report=rep)
         opt.step()
+        bad += TF.check_params(g, step, dict(m.named_parameters()), report=rep)
     sd = m.state_dict()
-    worst = 0.0
-    gmax = max(float(g['gsum0/' + k][0]) for k in meta['names'])
-    for k in meta['names']:
-        if float(g['gsum0/' + k][0]) < 1e-5 * gmax:
-            continue                                      # noise-level gradient: Adam moves the parameter by +-lr at random
-        _, ent = TF.digest(sd[k], g['idx/' + k])
-        d = float(np.abs(ent - g['pent/' + k]).max())
-        worst = max(worst, d)
-        if not d < 2e-5:                                  # parameters after the Adam steps, at the large-|g| entries
-            bad.append(('parameter after the steps', k, d))
+    last = TF.self_noise(g, meta['nsteps'] - 1)
+    stat_tol = 1e-4 if (last is None or meta['nsteps'] == 1) else max(1e-4, 3.0 * last[1])
     for k in sd:
         if 'running_' in k:
             ref = g['stat/' + k]
-            if not np.abs(sd[k].cpu().numpy() - ref).max() < 1e-4 * max(1.0, np.abs(ref).max()):
+            if not np.abs(sd[k].cpu().numpy() - ref).max() < stat_tol * max(1.0, np.abs(ref).max()):
                 bad.append(('running statistic', k))
         if 'num_batches' in k:
             assert int(sd[k]) == int(g['stat/' + k])
-    rep.append('post-step parameters: max |delta| at the fingerprint entries %.3g' % worst)
     _report('train_fixture_report.txt', rep)
     assert not bad, bad[:10]
 

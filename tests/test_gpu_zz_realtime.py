@@ -7,7 +7,7 @@ import torch
 
 from conftest import load_golden
 from gast_b200 import synth
-from gast_b200.realtime import CausalStream
+from gast_b200.realtime import CausalStream, WindowStream
 from test_gpu_parity import build_model, TOL
 
 pytestmark = pytest.mark.gpu
@@ -53,3 +53,31 @@ def test_causal_stream_vs_reference_golden(name):
     cs.reset()
     again = torch.stack([cs.push(torch.from_numpy(x[:, t]).cuda()) for t in range(5)], dim=1).cpu().numpy()
     assert np.abs(again - y[:, :5]).max() < TOL
+
+
+def test_o1_stream_matches_window_recompute_with_staggered_resets():
+    """the O(1) rings (CausalStream) against the recompute-the-window driver (WindowStream) on the same causal
+    network, with streams that restart at different times, wider than one ring revolution (81-frame model:
+    rings of 9, 27 and 81 slots)"""
+    from model.gast_net import SpatioTemporalModelOptimized1f
+    from test_gpu_parity import _adj
+    m = SpatioTemporalModelOptimized1f(_adj(17), 17, 2, 17, [3, 3, 3, 3], causal=True, dropout=0.05, channels=32)
+    synth.randomize_module(m, 12)
+    m = m.cuda().eval()
+    n, T = 5, 100
+    seqs = torch.from_numpy(synth.synth_input(n, T, 17, 2, seed=31)).cuda()
+    a, b = CausalStream(m, n), WindowStream(m, n)
+    assert a.push(seqs[:, 0]).shape == (n, 17, 3)
+    a.reset(); b_out = None
+    worst = 0.0
+    for t in range(T):
+        if t == 37:
+            a.reset([1, 3]); b.reset([1, 3])
+        if t == 90:
+            a.reset([0]); b.reset([0])
+        ya, yb = a.push(seqs[:, t]), b.push(seqs[:, t])
+        worst = max(worst, (ya - yb).abs().max().item())
+    assert worst < 2e-5, worst
+    assert a.last_launches < 60                       # one position per layer: ~40 launches per frame, any n
+    with pytest.raises(RuntimeError, match='causal'):
+        CausalStream(SpatioTemporalModelOptimized1f(_adj(17), 17, 2, 17, [3, 3, 3], channels=32).cuda().eval(), 2)

@@ -174,6 +174,8 @@ def test_torch_ref_training_matches_reference_fixture(name):
         loss = TR.mpjpe(y, tgt)
         loss.backward()
         # same ATen kernels in the same order as the reference modules: agreement is at rounding level
+        # same ATen kernels in the same order as the reference modules: step 0 agrees at rounding level; later
+        # steps to the reference's own thread-count noise (train_fixture.check_step)
         bad = TF.check_step(g, step, y.detach().numpy(), loss.item(), {k: p[k].grad for k in meta['names']},
                             y_tol=2e-6, loss_rtol=1e-6, ent_rtol=2e-3, norm_rtol=2e-3)
         assert not bad, bad[:10]
@@ -184,5 +186,7 @@ def test_torch_ref_training_matches_reference_fixture(name):
                     assert np.abs(p[k].grad.numpy() - gr).max() <= 2e-3 * np.abs(gr).max(), k
         opt.step()
     if nsteps == meta['nsteps']:
+        last = TF.self_noise(g, nsteps - 1)
+        tol = 1e-5 if (last is None or nsteps == 1) else max(1e-5, 3.0 * last[1])
         for k, v in stats.items():
-            assert np.abs(v.numpy() - g['stat/' + k]).max() < 1e-5 * max(1.0, np.abs(g['stat/' + k]).max()), k
+            assert np.abs(v.numpy() - g['stat/' + k]).max() < tol * max(1.0, np.abs(g['stat/' + k]).max()), k

@@ -1,10 +1,10 @@
-"""CPU: the ring-buffer windowing of gast_b200.realtime.CausalStream against the reference's causal padding
+"""CPU: the ring-buffer windowing of gast_b200.realtime.WindowStream (the generic O(rf)-per-frame driver) against the reference's causal padding
 (UnchunkedGenerator(pad, causal_shift=pad): common/generators.py:217-221), with a stub in place of the network
 (the network itself has no CPU path)."""
 import numpy as np
 import torch
 
-from gast_b200.realtime import CausalStream
+from gast_b200.realtime import WindowStream
 
 
 class WindowProbe(torch.nn.Module):
@@ -37,7 +37,7 @@ def test_causal_stream_windows_match_reference_padding():
     rf, J, T = 27, 17, 70
     seqs = rs.standard_normal((3, T, J, 2)).astype(np.float32)
     probe = WindowProbe(rf, J)
-    cs = CausalStream(probe, n_streams=3, device='cpu')
+    cs = WindowStream(probe, n_streams=3, device='cpu')
     outs = []
     for t in range(T):
         outs.append(cs.push(seqs[:, t]).numpy().copy())

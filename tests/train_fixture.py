@@ -38,15 +38,36 @@ def digest(t, idx):
     return np.array([float(f.norm()), float(f.sum())], np.float64), f[torch.from_numpy(idx)].numpy().astype(np.float32)
 
 
-def check_step(g, step, y, loss, grads, y_tol, loss_rtol, ent_rtol, norm_rtol, report=None):
+def self_noise(g, step):
+    """the reference's own run-to-run band at this step (the same run with 3 instead of 8 CPU threads; see
+    make_golden.py:train_case): (loss rel, max|dy|, max|dparam|, worst gradient rel. L2).  None for fixtures
+    without the alternate run."""
+    if ('alt_loss%d' % step) not in g:
+        return None
+    lr = float(g['loss%d' % step])
+    return (abs(float(g['alt_loss%d' % step]) - lr) / abs(lr), float(g['alt_dy%d' % step]), float(g['alt_dp%d' % step]),
+            float(g['alt_dg%d' % step]))
+
+
+def check_step(g, step, y, loss, grads, y_tol, loss_rtol, ent_rtol, norm_rtol, report=None, band_factor=3.0):
     """compare one step of an implementation with the fixture.  grads: name -> tensor.
-    ent_rtol: tolerance on the stored large-|g| entries relative to the largest of them;
-    norm_rtol: tolerance on ||g||.  Every violation is collected (and reported) before the assert."""
+    ent_rtol: tolerance on the stored large-|g| entries relative to the largest of them; norm_rtol: on ||g||.
+    Step 0 (identical weights) is held to the given tolerances.  From step 1 on the weights have been through
+    Adam(amsgrad), whose first updates are lr*g/(|g|+eps): parameters whose gradient is rounding noise move by +-lr
+    at random, and two runs of the REFERENCE ITSELF (8 vs 3 CPU threads) no longer agree -- those steps are held to
+    `band_factor` x that measured self-noise of the reference (stored in the fixture), never tighter than the
+    step-0 tolerances.  Every violation is collected (and reported) before the assert."""
     bad = []
+    band = self_noise(g, step) if step > 0 else None
+    if band is not None:
+        loss_rtol = max(loss_rtol, band_factor * band[0])
+        y_abs = max(y_tol, band_factor * band[1])
+        ent_rtol = max(ent_rtol, band_factor * band[3])
+        norm_rtol = max(norm_rtol, band_factor * band[3])
     yr = g['y%d' % step]
     scale = max(1.0, float(np.abs(yr).max()))
     ey = float(np.abs(y - yr).max())
-    if not ey < y_tol * scale:
+    if not ey < (y_tol * scale if band is None else max(y_tol * scale, y_abs)):
         bad.append(('y', step, ey))
     lr = float(g['loss%d' % step])
     el = abs(loss - lr) / abs(lr)
@@ -72,10 +93,37 @@ def check_step(g, step, y, loss, grads, y_tol, loss_rtol, ent_rtol, norm_rtol, r
         if not ee < ent_rtol:
             bad.append(('grad entries', step, k, ee))
     if report is not None:
-        report.append(('step %d: max|dy| %.3g  loss rel %.3g  worst grad fingerprint %.3g (%s)  violations %d'
-                       % (step, ey, el, worst[0], worst[1], len(bad))))
+        report.append(('step %d: max|dy| %.3g  loss rel %.3g  worst grad fingerprint %.3g (%s)  violations %d%s'
+                       % (step, ey, el, worst[0], worst[1], len(bad),
+                          '' if band is None else '   [reference self-noise at this step: loss rel %.3g, max|dy| %.3g, '
+                                                  'gradient rel L2 %.3g]' % (band[0], band[1], band[3]))))
         report.extend('   ' + repr(b) for b in bad[:20])
     return bad
 
 
-__all__ = ['load_golden', 'build_module', 'batch', 'digest', 'check_step', 'adj_t']
+def check_params(g, step, params, report=None, band_factor=3.0):
+    """parameters after optimizer step `step`, at the fingerprint entries whose step-0 gradient is well above the fp32
+    gradient noise (|g| > 0.1 max|g| of the tensor: Adam's first update is lr*sign(g), a noise-level entry moves by
+    +-lr at random).  After step 0: 2e-5 absolute.  Later: band_factor x the reference's self-noise."""
+    bad = []
+    band = self_noise(g, step)
+    tol = 2e-5 if (step == 0 or band is None) else max(2e-5, band_factor * band[2])
+    worst = 0.0
+    gmax = max(float(g['gsum0/' + k][0]) for k in g['meta']['names'])
+    for k in g['meta']['names']:
+        if float(g['gsum0/' + k][0]) < 1e-5 * gmax:
+            continue
+        g0 = np.abs(g['gent0/' + k])
+        sel = g0 > 0.1 * g0.max()
+        _, ent = digest(params[k], g['idx/' + k])
+        d = float(np.abs(ent - g['pent%d/%s' % (step, k)])[sel].max())
+        worst = max(worst, d)
+        if not d < tol:
+            bad.append(('parameter after step %d' % step, k, d))
+    if report is not None:
+        report.append('parameters after step %d: max |delta| at the well-conditioned fingerprint entries %.3g (tolerance %.3g)'
+                      % (step, worst, tol))
+    return bad
+
+
+__all__ = ['load_golden', 'build_module', 'batch', 'digest', 'check_step', 'check_params', 'self_noise', 'adj_t']
