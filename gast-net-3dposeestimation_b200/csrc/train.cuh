@@ -55,19 +55,22 @@ static int seg_gemm(TCtx& c, const ASeg* segs, int nseg, const float* W, int ldw
 
 static long long pad32(long long m) { return (m + 31) / 32 * 32; }
 
-// dW[N][K] = dZ[M][N]^T . A[M][K]   via two transposes and the NT kernel (K' = M padded to 32)
+// dW[N][K] = dZ[M][N]^T . A[M][K]: split over the rows (wgrad_tn_kernel) + fixed-order reduction of the partials
 static int dense_tn(TCtx& c, const float* dZ, int lddz, const float* A, int lda, long long M, int N, int K, float* dW,
                     int lddw) {
-  const long long Mp = pad32(M);
-  float* dZt = c.fl((size_t)N * Mp);
-  float* At = c.fl((size_t)K * Mp);
-  if (c.dry) return 0;
-  cudaMemsetAsync(dZt, 0, sizeof(float) * (size_t)N * Mp, c.st);
-  cudaMemsetAsync(At, 0, sizeof(float) * (size_t)K * Mp, c.st);
-  dim3 tb(32, 8);
-  transpose_kernel<<<dim3(cdiv(M, 32), cdiv(N, 32)), tb, 0, c.st>>>(dZ, M, N, lddz, dZt, Mp);
-  transpose_kernel<<<dim3(cdiv(M, 32), cdiv(K, 32)), tb, 0, c.st>>>(A, M, K, lda, At, Mp);
-  return dense_nt(c, dZt, (int)Mp, At, N, K, (int)Mp, dW, lddw);
+  const int tiles = (int)(cdiv(N, WG_T) * cdiv(K, WG_T));
+  // enough CTAs for two waves of the machine, at least 256 rows per split
+  long long S = std::max<long long>(1, std::min<long long>((M + 255) / 256, (2LL * c.h->sm_count + tiles - 1) / tiles));
+  long long rps = ((M + S - 1) / S + WG_M - 1) / WG_M * WG_M;
+  S = (M + rps - 1) / rps;
+  if (S < 1) S = 1;
+  float* part = c.fl((size_t)S * N * K);
+  if (c.dry || M <= 0) return 0;
+  dim3 grid(cdiv(N, WG_T), cdiv(K, WG_T), (unsigned)S);
+  wgrad_tn_kernel<<<grid, 256, 0, c.st>>>(dZ, lddz, A, lda, M, N, K, rps, part);
+  wgrad_reduce_kernel<<<cdiv((long long)N * K, 256), 256, 0, c.st>>>(part, (int)S, N, K, dW, lddw);
+  c.h->launches += 2;
+  return 0;
 }
 
 // dA[M][K] = dZ[M][N] . W[N][K]   (W transposed on the fly)

@@ -156,6 +156,115 @@ __global__ void d2f_kernel(const double* __restrict__ in, float* __restrict__ ou
 // ----------------------------------------------------------------------------------------------
 // layout helpers
 // ----------------------------------------------------------------------------------------------
+// Weight gradient  dW[N][K] = dZ[M][N]^T . A[M][K]  ("TN" GEMM: the contraction runs over the ROWS of both
+// operands, so both tiles are read in their natural row-major form -- no transposed copies).  The training batch
+// makes M the only large dimension (b=128: M = 19,584 rows against N x K = 256 x 384), so the work is split over
+// M: grid = (N tiles, K tiles, S row ranges); split s writes its partial [N][K] product to part + s*N*K and
+// wgrad_reduce_kernel sums the S partials in a fixed order (deterministic, unlike atomics).
+// 128 x 128 tile, 256 threads, 8 x 8 micro-tiles as 2 x 2 blocks of 4 x 4 (conflict-free 128-bit smem reads),
+// rows staged 16 at a time with register prefetch.  Exact fp32 (FFMA).
+constexpr int WG_T = 128, WG_M = 16;
+__global__ void __launch_bounds__(256)
+wgrad_tn_kernel(const float* __restrict__ dZ, int lddz, const float* __restrict__ A, int lda, long long M, int N, int K,
+                long long rows_per_split, float* __restrict__ part) {
+  __shared__ __align__(16) float sZ[2][WG_M][WG_T];
+  __shared__ __align__(16) float sA[2][WG_M][WG_T];
+  const int n0 = blockIdx.x * WG_T, k0 = blockIdx.y * WG_T;
+  const long long m_beg = (long long)blockIdx.z * rows_per_split;
+  const long long m_end = min(M, m_beg + rows_per_split);
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  // loader: thread -> (row lr of the 16-row slab, 16-byte column group lc): 16 rows x 32 float4 = 512 float4 per
+  // operand, 2 per thread
+  const int lr = tid >> 5, lc = (tid & 31) * 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const bool vecZ = (lddz % 4 == 0) && ((reinterpret_cast<uintptr_t>(dZ) & 15) == 0);
+  const bool vecA = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  auto load4 = [&](const float* base, int ld, long long m, int c, int lim, bool vec) -> float4 {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < m_end) {
+      const float* p = base + m * ld + c;
+      if (vec && c + 3 < lim) v = ldg4(p);
+      else {
+        if (c < lim) v.x = __ldg(p);
+        if (c + 1 < lim) v.y = __ldg(p + 1);
+        if (c + 2 < lim) v.z = __ldg(p + 2);
+        if (c + 3 < lim) v.w = __ldg(p + 3);
+      }
+    }
+    return v;
+  };
+  float4 rz[2], ra[2];
+  auto fetch = [&](long long m0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      rz[h] = load4(dZ, lddz, m0 + lr + 8 * h, n0 + lc, N, vecZ);
+      ra[h] = load4(A, lda, m0 + lr + 8 * h, k0 + lc, K, vecA);
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      *reinterpret_cast<float4*>(&sZ[buf][lr + 8 * h][lc]) = rz[h];
+      *reinterpret_cast<float4*>(&sA[buf][lr + 8 * h][lc]) = ra[h];
+    }
+  };
+  int buf = 0;
+  if (m_beg < m_end) {
+    fetch(m_beg);
+    stash(0);
+  }
+  __syncthreads();
+  for (long long m0 = m_beg; m0 < m_end; m0 += WG_M) {
+    const bool more = m0 + WG_M < m_end;
+    if (more) fetch(m0 + WG_M);
+#pragma unroll
+    for (int mm = 0; mm < WG_M; ++mm) {
+      const float4 z0 = *reinterpret_cast<const float4*>(&sZ[buf][mm][ty * 4]);
+      const float4 z1 = *reinterpret_cast<const float4*>(&sZ[buf][mm][64 + ty * 4]);
+      const float4 a0 = *reinterpret_cast<const float4*>(&sA[buf][mm][tx * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sA[buf][mm][64 + tx * 4]);
+      const float zv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(zv[i], av[j], acc[i][j]);
+    }
+    if (more) stash(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  float* out = part + (long long)blockIdx.z * N * K;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int n = n0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (n >= N) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int k = k0 + jh * 64 + tx * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (k + j < K) out[(long long)n * K + k + j] = acc[i][jh * 4 + j];
+    }
+  }
+}
+
+// dW[n][k] (leading dim lddw) = sum over the S partial products, in split order
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int S, int N, int K, float* __restrict__ dW, int lddw) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long NK = (long long)N * K;
+  if (idx >= NK) return;
+  float s = 0.f;
+  for (int i = 0; i < S; ++i) s += part[(long long)i * NK + idx];
+  const int n = (int)(idx / K);
+  dW[(long long)n * lddw + (idx - (long long)n * K)] = s;
+}
+
+// ----------------------------------------------------------------------------------------------
 // out[c][r] = in[r][c]   (in: R x C with leading dim ldi; out: C x ldo, columns r >= R zero-filled by memset)
 __global__ void transpose_kernel(const float* __restrict__ in, long long R, int C, int ldi, float* __restrict__ out,
                                  long long ldo) {

@@ -7,6 +7,7 @@ cd "$(dirname "$0")/.."
 rm -rf .stage
 mkdir -p .stage gpurun_out
 cp -r gast-net-3dposeestimation_b200 tests tools oracle include profiles bench.py __graft_entry__.py .stage/
+[ -d baseline ] && cp -r baseline .stage/
 [ -f MEASURED_PEAKS.json ] && cp MEASURED_PEAKS.json .stage/
 find .stage -name __pycache__ -prune -exec rm -rf {} +
 ln -s ../gpurun_out .stage/gpurun_out
