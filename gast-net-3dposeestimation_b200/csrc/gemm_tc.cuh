@@ -48,8 +48,14 @@ struct TcWeights {
 };
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;
-constexpr int TC_BSTAGES = 3;   // B (weights) ring in shared memory, filled by TMA
-constexpr int TC_RSTAGES = 4;   // raw A ring in shared memory, filled by TMA or cp.async (no register staging, no MSHR cap)
+#ifndef GAST_TC_BSTAGES
+#define GAST_TC_BSTAGES 3
+#endif
+#ifndef GAST_TC_RSTAGES
+#define GAST_TC_RSTAGES 4
+#endif
+constexpr int TC_BSTAGES = GAST_TC_BSTAGES;   // B (weights) ring in shared memory, filled by TMA
+constexpr int TC_RSTAGES = GAST_TC_RSTAGES;   // raw A ring in shared memory, filled by TMA or cp.async (no register staging, no MSHR cap)
 constexpr int TC_ASTAGES = 2;   // A (activations) ring in TENSOR MEMORY, filled by tcgen05.st
 constexpr int TC_FLUSH = 4;     // K chunks accumulated in TMEM before the sum is flushed to registers
 #ifndef GAST_TC_CLUSTER
@@ -72,6 +78,13 @@ static_assert(TC_REG_A + 2 * TC_REG_E + TC_REG_M <= 512, "register file over-sub
 #define GAST_TC_PROBE_K 3
 #endif
 constexpr int TC_PROBE_K = GAST_TC_PROBE_K;
+// A converters (TMA-fed path): 1 = software-pipelined -- the raw rows of chunk c+1 are requested from shared memory
+// before the hand-over of chunk c (wait for the tensor-memory stage, tcgen05.st, arrive), so the shared-memory
+// latency and the wait for the TMA data overlap the hand-over latencies; 0 = one chunk at a time (round 1)
+#ifndef GAST_TC_CONV_PIPE
+#define GAST_TC_CONV_PIPE 1
+#endif
+constexpr int TC_CONV_PIPE = GAST_TC_CONV_PIPE;
 constexpr int TC_EN = 64;         // accumulator columns owned by one epilogue warpgroup
 constexpr int TC_STAGE_BYTES = 2 * 16384;            // B_hi, B_lo : 128 rows x 128 B each
 constexpr int TC_SLD = 68;                            // SemCH coefficient slab row stride (floats): 64 channels + 4, conflict-free 16B rows
@@ -317,7 +330,8 @@ constexpr uint32_t TC_IDESC_BF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t
 // ----------------------------------------------------------------------------------------
 // DBG != 0 builds timing-experiment variants (tools/tc_probe.py --perf): 1 = no TMEM->register
 // flush, 2 = no global A loads, 3 = main MMA only, 4 = no tcgen05.st of A, 5 = 1+2+4,
-// 6 = full kernel + clock64() attribution of every role's waits (written to p.dbg[blockIdx.x*32 + i]).
+// 6 = full kernel + clock64() attribution of every role's waits (written to p.dbg[blockIdx.x*32 + i]),
+// 7 = correction (bf16) MMAs only.
 template <int EPI, int DBG = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensorMap map_hi,
@@ -473,6 +487,57 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     }
     const int my_row = warp * 32 + lane;
     const bool row_in_box = my_row < p.fpt * J;
+    // raw rows of one chunk -> 8 float4 of this thread's row (swizzle-aware, conflict-free)
+    auto load_raw = [&](int slot_, float4 (&xr)[8]) {
+      const float* rowp = reinterpret_cast<const float*>(smem + TC_OFF_XPOSE + slot_ * 16384 + my_row * 128);
+      const int sw = my_row & 7;              // TMA SWIZZLE_128B: 16-byte chunk index ^= row % 8
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        xr[i] = *reinterpret_cast<const float4*>(rowp + ((i ^ sw) << 2));
+        if (!row_in_box) xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // rows the box does not cover
+      }
+    };
+    auto split_row = [&](const float4 (&xr)[8], uint32_t* hi, uint32_t* lo) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 x = xr[i];
+        const float h0 = tf32_rn_fast(x.x), h1 = tf32_rn_fast(x.y), h2 = tf32_rn_fast(x.z), h3 = tf32_rn_fast(x.w);
+        hi[4 * i + 0] = __float_as_uint(h0); hi[4 * i + 1] = __float_as_uint(h1);
+        hi[4 * i + 2] = __float_as_uint(h2); hi[4 * i + 3] = __float_as_uint(h3);
+        lo[2 * i + 0] = pack_bf16x2(x.x - h0, x.y - h1);
+        lo[2 * i + 1] = pack_bf16x2(x.z - h2, x.w - h3);
+        lo[16 + 2 * i + 0] = pack_bf16x2(h0, h1);
+        lo[16 + 2 * i + 1] = pack_bf16x2(h2, h3);
+      }
+    };
+    if (atma && TC_CONV_PIPE && DBG == 0) {
+      float4 xr[8];
+      if (my_chunks > 0) {
+        mbar_wait(bar0 + BR_FULL + 8 * slot, rphase);
+        load_raw(slot, xr);
+      }
+      for (long long c = 0; c < my_chunks; ++c) {
+        uint32_t hi[32], lo[32];
+        split_row(xr, hi, lo);                 // consumes every raw value: the shared-memory reads are complete
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + BR_EMPTY + 8 * slot);   // raw slot free for the TMA producer
+        if (++slot == TC_RSTAGES) { slot = 0; rphase ^= 1; }
+        if (c + 1 < my_chunks) {               // next chunk's rows on their way while this one is handed over
+          mbar_wait(bar0 + BR_FULL + 8 * slot, rphase);
+          load_raw(slot, xr);
+        }
+        mbar_wait(bar0 + BA_EMPTY + 8 * stage, phase ^ 1);
+        tc_fence_after();
+        const uint32_t ta = tmem_base + lane_off + TC_A_COL + stage * 64;
+        tmem_st32(ta, hi);
+        tmem_st32(ta + 32, lo);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + BA_FULL + 8 * stage);
+        if (++stage == TC_ASTAGES) { stage = 0; phase ^= 1; }
+      }
+    } else
     for (long long c = 0; c < my_chunks; ++c) {
       long long tq0 = 0;
       if (DBG == 6) tq0 = clock64();
@@ -646,9 +711,10 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           for (int k = 0; k < TC_BK / 8; ++k) {
             if (elect_one()) {
               const uint64_t adv = (uint64_t)(k * 2);      // 8 fp32 = 32 B = 2 x 16 B
-              umma_tf32_ts(d_main, a_hi + 8 * k, b_hi + adv, TC_IDESC, (cg | k) ? 1u : 0u);
+              if (DBG != 7) umma_tf32_ts(d_main, a_hi + 8 * k, b_hi + adv, TC_IDESC, (cg | k) ? 1u : 0u);
               // correction: bf16 k-step k of the K=64 row [A_lo | A_hi] . [B_hi | B_lo]^T (8 columns of bf16
-              // pairs in tensor memory, 32 bytes of the swizzled B row, like a tf32 k-step)
+              // pairs in tensor memory, 32 bytes of the swizzled B row, like a tf32 k-step).  (Issuing the four
+              // tf32 MMAs first and the four bf16 ones after them measured 5 % slower than interleaving them.)
               if (DBG != 3) umma_bf16_ts(d_corr, a_pk + 8 * k, b_pk + adv, TC_IDESC_BF, (c | k) ? 1u : 0u);
               if (k == TC_BK / 8 - 1) {
                 if (TC_CLUSTER > 1) umma_commit_mc(bar0 + BB_EMPTY + 8 * bs, (uint16_t)((1u << TC_CLUSTER) - 1));
@@ -1298,6 +1364,7 @@ inline int tc_launch(int sm_count, cudaStream_t st, int epi, const GemmP& p, con
       case 4: return tc_launch_one<EPI_PLAIN, 4>(grid, st, p, t, nt, (int)items);
       case 5: return tc_launch_one<EPI_PLAIN, 5>(grid, st, p, t, nt, (int)items);
       case 6: return tc_launch_one<EPI_PLAIN, 6>(grid, st, p, t, nt, (int)items);
+      case 7: return tc_launch_one<EPI_PLAIN, 7>(grid, st, p, t, nt, (int)items);
       default: return (int)cudaErrorInvalidValue;
     }
   }

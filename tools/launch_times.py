@@ -15,13 +15,19 @@ from model.gast_net import SpatioTemporalModel  # noqa: E402
 
 
 def main():
+    # usage: launch_times.py [clips [joints [channels [filter,widths]]]]
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-    J = 17
+    J = int(sys.argv[2]) if len(sys.argv) > 2 else 17
+    ch = int(sys.argv[3]) if len(sys.argv) > 3 else 128
+    fw = [int(v) for v in sys.argv[4].split(',')] if len(sys.argv) > 4 else [3, 3, 3]
+    T = 1
+    for v in fw:
+        T *= v
     adj = adj_mx_from_skeleton(Skeleton(synth.skeleton_parents(J), [], []))
-    m = SpatioTemporalModel(adj, J, 2, J, [3, 3, 3], channels=128)
+    m = SpatioTemporalModel(adj, J, 2, J, fw, channels=ch)
     synth.randomize_module(m, 3)
     m = m.cuda().eval()
-    x = torch.from_numpy(synth.synth_input(B, 27, J, 2, seed=5)).cuda()
+    x = torch.from_numpy(synth.synth_input(B, T, J, 2, seed=5)).cuda()
     with torch.no_grad():
         for _ in range(3):
             m(x)
