@@ -331,7 +331,8 @@ constexpr uint32_t TC_IDESC_BF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t
 // DBG != 0 builds timing-experiment variants (tools/tc_probe.py --perf): 1 = no TMEM->register
 // flush, 2 = no global A loads, 3 = main MMA only, 4 = no tcgen05.st of A, 5 = 1+2+4,
 // 6 = full kernel + clock64() attribution of every role's waits (written to p.dbg[blockIdx.x*32 + i]),
-// 7 = correction (bf16) MMAs only.
+// 7 = correction (bf16) MMAs only, 8 = 5 + no B loads (MMAs on stale shared memory), 9 = 8 + A converters reduced to
+// their barrier hand-shakes (no shared-memory reads, no split): the floor of the MMA issue loop and the barrier protocol.
 template <int EPI, int DBG = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensorMap map_hi,
@@ -465,7 +466,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       const uint32_t dst = raw0 + (uint32_t)(slot_ * 128 * TC_XLD * 4) + (uint32_t)(rsub * TC_XLD * 4 + c16 * 16);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const bool ok = roff[i] >= 0 && DBG != 2 && DBG != 5;
+        const bool ok = roff[i] >= 0 && DBG != 2 && DBG != 5 && DBG != 8 && DBG != 9;
         cp_async16(dst + (uint32_t)(4 * i * TC_XLD * 4), ok ? (const void*)(src + roff[i]) : (const void*)sgm.base,
                    ok ? 16u : 0u);
       }
@@ -558,7 +559,8 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       const int sw = atma ? (my_row & 7) : 0;   // TMA SWIZZLE_128B: 16-byte chunk index ^= row % 8
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float4 x = *reinterpret_cast<const float4*>(rowp + ((i ^ sw) << 2));
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (DBG != 9) x = *reinterpret_cast<const float4*>(rowp + ((i ^ sw) << 2));
         if (atma && !row_in_box) x = make_float4(0.f, 0.f, 0.f, 0.f);   // rows the box does not cover
         const float h0 = tf32_rn_fast(x.x), h1 = tf32_rn_fast(x.y), h2 = tf32_rn_fast(x.z), h3 = tf32_rn_fast(x.w);
         hi[4 * i + 0] = __float_as_uint(h0); hi[4 * i + 1] = __float_as_uint(h1);
@@ -583,7 +585,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       if (DBG == 6) { long long t1 = clock64(); tA_wait += t1 - t0; t0 = t1; ++tA_n; }
       tc_fence_after();
       const uint32_t ta = tmem_base + lane_off + TC_A_COL + stage * 64;
-      if (DBG != 4 && DBG != 5) {
+      if (DBG != 4 && DBG != 5 && DBG != 8 && DBG != 9) {
         tmem_st32(ta, hi);
         tmem_st32(ta + 32, lo);
         tmem_wait_st();
@@ -618,6 +620,11 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           mbar_wait(bar0 + BB_EMPTY + 8 * stage, phase ^ 1);     // every CTA of the cluster consumed it
           if (DBG == 6) tB_wait += clock64() - t0;
           const uint32_t full = bar0 + BB_FULL + 8 * stage;
+          if (DBG == 8 || DBG == 9) {                            // experiment: MMAs on stale smem, no B traffic
+            mbar_arrive(full);
+            if (++stage == TC_BSTAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(full, 2 * 16384);                // own share + the peers' shares
           if (TC_CLUSTER > 1) {
             // this CTA fetches rows [R*rank, R*rank+R) of the 128-row B tile (hi and lo) and
@@ -655,6 +662,11 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
             const CUtensorMap* mp = (mi == 0) ? &amap0 : (mi == 1) ? &amap1 : &amap2;
             mbar_wait(bar0 + BR_EMPTY + 8 * slot, rphase ^ 1);
             const uint32_t full = bar0 + BR_FULL + 8 * slot;
+            if (DBG == 8 || DBG == 9) {                      // experiment: no A traffic
+              mbar_arrive(full);
+              if (++slot == TC_RSTAGES) { slot = 0; rphase ^= 1; }
+              continue;
+            }
             mbar_arrive_expect_tx(full, bytes);
             // box {32 channels, J joints, fpt frames} -> fpt*J dense 128-byte rows, swizzled;
             // frames past the end of the tensor are zero-filled (ragged last tile, dummy tiles)
@@ -832,7 +844,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       // with the first group when K is a single flush group made ptxas spill ~175 registers.)
       float acc[TC_EN];
       const int ngroups = (nchunks + TC_FLUSH - 1) / TC_FLUSH;
-      const bool noflush = (DBG == 1 || DBG == 5);
+      const bool noflush = (DBG == 1 || DBG == 5 || DBG == 8 || DBG == 9);
       {
         const uint32_t mb = mcount % NMAIN;
         long long t0 = 0;
@@ -1365,6 +1377,8 @@ inline int tc_launch(int sm_count, cudaStream_t st, int epi, const GemmP& p, con
       case 5: return tc_launch_one<EPI_PLAIN, 5>(grid, st, p, t, nt, (int)items);
       case 6: return tc_launch_one<EPI_PLAIN, 6>(grid, st, p, t, nt, (int)items);
       case 7: return tc_launch_one<EPI_PLAIN, 7>(grid, st, p, t, nt, (int)items);
+      case 8: return tc_launch_one<EPI_PLAIN, 8>(grid, st, p, t, nt, (int)items);
+      case 9: return tc_launch_one<EPI_PLAIN, 9>(grid, st, p, t, nt, (int)items);
       default: return (int)cudaErrorInvalidValue;
     }
   }

@@ -45,7 +45,7 @@ def perf():
         mma_bound = (2.0 if b"bf16-corr" in lib.gast_version() else 3.0) * (-(-M // 128) * 128) * (-(-N // 128) * 128) * K / (2048.0 * 148 * 1.9e9) * 1e3
         line = 'M=%d N=%d K=%d  MMA-bound %.3f ms |' % (M, N, K, mma_bound)
         for core, mode, name in ((1, 0, 'ffma'), (0, 0, 'tc'), (0, 1, 'noflush'), (0, 2, 'noAload'), (0, 3, 'mainonly'),
-                                 (0, 4, 'noSTTM'), (0, 5, 'mma+B only'), (0, 7, 'corr-only'), (0, 17, 'grouped-order')):
+                                 (0, 4, 'noSTTM'), (0, 5, 'mma+B only'), (0, 7, 'corr-only'), (0, 8, 'mma-only(no A/B traffic)'), (0, 9, 'mma+barriers only')):
             ms = C.c_float(0)
             rc = lib.gast_debug_gemm(a.data_ptr(), w.data_ptr(), o.data_ptr(), M, N, K, core, mode, 5, C.byref(ms),
                                      torch.cuda.current_stream().cuda_stream)
@@ -105,7 +105,6 @@ def main():
             ref = A.astype(np.float64) @ W.astype(np.float64).T
             stats('K=%4d %-8s FFMA fp32' % (K, kind), gemm(A, W, 1, 0), ref)
             stats('K=%4d %-8s tcgen05 tf32+bf16corr' % (K, kind), gemm(A, W, 0, 0), ref)
-            stats('K=%4d %-8s tcgen05 grouped issue order' % (K, kind), gemm(A, W, 0, 17), ref)
             Ah, Wh = tf32_round(A), tf32_round(W)
             refh = Ah.astype(np.float64) @ Wh.astype(np.float64).T
             stats('K=%4d %-8s tcgen05 hi.hi vs exact(hi.hi)' % (K, kind), gemm(Ah, Wh, 0, 0), refh)
