@@ -92,6 +92,7 @@ struct gast_handle {
   float *We = nullptr, *be = nullptr;
   bool prepared = false;
   bool stream_ready = false;         // tap-rotated stage weights match the current parameters
+  unsigned long long* dropout_state = nullptr;   // caller-owned device counter added to the dropout seed (graph replays)
   int launches = 0;
   int tc_launches = 0;
   int gemm_core = 0;                 // 0 auto (tcgen05 where possible), 1 force FFMA
@@ -974,8 +975,15 @@ extern "C" int gast_forward_train(gast_t* h, const float* x, float* y, int32_t B
   if (train_forward(h, c, ts, x, y, B, T)) { h->trains.pop_back(); return 1; }
   ts.arena_off = a.off;
   ts.valid = true;
+  if (h->dropout_state && dropout_p > 0.f) dropout_bump_kernel<<<1, 1, 0, st>>>(h->dropout_state);
   h->prepared = false;      // running statistics changed: eval constants are stale
   CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gast_set_dropout_state(gast_t* h, void* dev_u64) {
+  if (!h) return fail("gast_set_dropout_state: null handle");
+  h->dropout_state = reinterpret_cast<unsigned long long*>(dev_u64);
   return 0;
 }
 

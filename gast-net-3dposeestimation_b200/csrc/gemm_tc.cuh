@@ -26,10 +26,15 @@
 // Two-level accumulation.  Measured on B200 (tools/tc_probe.py, profiles/r01_tc_numerics.md): the
 // tensor core aligns and TRUNCATES its addends, so a long accumulation chain in TMEM is biased
 // towards zero by ~1 ulp per MMA (K=1536: -1e-5 relative; whole model: 6e-5 abs, MPJPE biased).
-// Therefore the big term A_hi.B_hi is accumulated in TMEM over at most TC_FLUSH chunks (into a ring
-// of 2 main buffers) and the group sums are added in registers with RN; the small terms
-// A_lo.B_hi + A_hi.B_lo (2^-11 of the result, truncation harmless) accumulate over the whole K in
-// a third TMEM buffer that is added once per tile.
+// Therefore a tile is accumulated in TMEM over at most TC_FLUSH chunks at a time (into a ring of 2
+// accumulator buffers) and the group sums are added in registers with RN.  The correction products
+// A_lo.B_hi + A_hi.B_lo (2^-11 of the result) go into the SAME accumulator as A_hi.B_hi (round 1 kept them in
+// a third TMEM buffer over the whole K): that frees 128 tensor-memory columns, which buy a 4-stage instead of a
+// 2-stage A ring -- the hand-over latency converter -> MMA -> converter of a 2-stage ring, not the tensor pipe,
+// bounded the chunk rate at ~800 cycles (profiles/r02_tc_attribution_bf16corr.md) -- and it removes the
+// per-tile wait for the correction buffer to drain.  Every MMA truncates the accumulator once whatever the size
+// of its addend, so a group now sees 8 truncations per chunk instead of 4; the pre-compensation through W_lo
+// (tc_split_kernel) counts them accordingly.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -56,7 +61,11 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;
 #endif
 constexpr int TC_BSTAGES = GAST_TC_BSTAGES;   // B (weights) ring in shared memory, filled by TMA
 constexpr int TC_RSTAGES = GAST_TC_RSTAGES;   // raw A ring in shared memory, filled by TMA or cp.async (no register staging, no MSHR cap)
-constexpr int TC_ASTAGES = 2;   // A (activations) ring in TENSOR MEMORY, filled by tcgen05.st
+#ifndef GAST_TC_ASTAGES
+#define GAST_TC_ASTAGES 4
+#endif
+constexpr int TC_ASTAGES = GAST_TC_ASTAGES;   // A (activations) ring in TENSOR MEMORY, filled by tcgen05.st (<= 4: 64 columns each)
+static_assert(TC_ASTAGES >= 2 && TC_ASTAGES <= 4, "the A ring has 256 tensor-memory columns");
 constexpr int TC_FLUSH = 4;     // K chunks accumulated in TMEM before the sum is flushed to registers
 #ifndef GAST_TC_CLUSTER
 #define GAST_TC_CLUSTER 2
@@ -71,13 +80,7 @@ constexpr int TC_THREADS = 512;   // 4 warpgroups: A converters | epilogue (cols
 #endif
 constexpr int TC_REG_A = GAST_TC_REG_A, TC_REG_E = GAST_TC_REG_E, TC_REG_M = GAST_TC_REG_M;
 static_assert(TC_REG_A + 2 * TC_REG_E + TC_REG_M <= 512, "register file over-subscribed");
-// k-step after which the MMA warp probes the barriers of the NEXT chunk: 3 = after the last MMA of the chunk
-// (the operands are surely there by then, and the probes overlap the MMAs still queued in the tensor pipe);
-// 1 = early (the probes often failed and a blocking wait followed at the top of the next chunk)
-#ifndef GAST_TC_PROBE_K
-#define GAST_TC_PROBE_K 3
-#endif
-constexpr int TC_PROBE_K = GAST_TC_PROBE_K;
+
 // A converters (TMA-fed path): 1 = software-pipelined -- the raw rows of chunk c+1 are requested from shared memory
 // before the hand-over of chunk c (wait for the tensor-memory stage, tcgen05.st, arrive), so the shared-memory
 // latency and the wait for the TMA data overlap the hand-over latencies; 0 = one chunk at a time (round 1)
@@ -85,6 +88,8 @@ constexpr int TC_PROBE_K = GAST_TC_PROBE_K;
 #define GAST_TC_CONV_PIPE 1
 #endif
 constexpr int TC_CONV_PIPE = GAST_TC_CONV_PIPE;
+
+
 constexpr int TC_EN = 64;         // accumulator columns owned by one epilogue warpgroup
 constexpr int TC_STAGE_BYTES = 2 * 16384;            // B_hi, B_lo : 128 rows x 128 B each
 constexpr int TC_SLD = 68;                            // SemCH coefficient slab row stride (floats): 64 channels + 4, conflict-free 16B rows
@@ -310,13 +315,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 // Tensor-memory map (512 columns x 128 lanes x 32 bit):
-//   [0,256)   main accumulator ring (2 x 128): A_hi.B_hi of ONE 32-wide K chunk
-//   [256,384) correction accumulator: A_lo.B_hi + A_hi.B_lo over the whole K
-//   [384,512) A operand ring (2 stages x {hi: 32 tf32 columns | 16 columns of bf16 pairs of lo | 16 of hi}):
+//   [0,256)   accumulator ring (2 x 128): A_hi.B_hi + A_lo.B_hi + A_hi.B_lo of one flush group (<= TC_FLUSH chunks)
+//   [256,512) A operand ring (4 stages x {hi: 32 tf32 columns | 16 columns of bf16 pairs of lo | 16 of hi}):
 //             row m in lane m, k along the columns
 constexpr uint32_t TC_NMAIN = 2;
-constexpr uint32_t TC_CORR_COL = 256;
-constexpr uint32_t TC_A_COL = 384;
+constexpr uint32_t TC_A_COL = 256;
 
 // instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=128
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
@@ -345,18 +348,21 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
   // A-producer samples were long-scoreboard stalls on generic loads from the patch).
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   unsigned char* smem = tc_smem_raw;
-  const uint32_t sbase = smem_u32(smem);
+  uint32_t sbase_ = smem_u32(smem);
+  // opaque to the optimiser: otherwise it re-derives the shared-window base from SR_CgaCtaId (a slow special-register
+  // read) in front of every mbarrier operation of the latency-bound MMA issue loop
+  asm volatile("" : "+r"(sbase_));
+  const uint32_t sbase = sbase_;
   if ((sbase & 1023u) != 0) __trap();   // SWIZZLE_128B atoms need 1024-byte alignment
   float* staging = reinterpret_cast<float*>(smem + TC_OFF_STAGING);
   float* ab_s = reinterpret_cast<float*>(smem + TC_OFF_AB);
   const uint32_t bar0 = sbase + TC_OFF_BAR;
-  // mbarriers (8 B each):  b_full[4] @0  b_empty[4] @32  a_full[2] @64  a_empty[2] @80
-  //                        main_full[2] @96  main_empty[2] @112  corr_full @128  corr_empty @136 ; tmem ptr @144
-  constexpr uint32_t BB_FULL = 0, BB_EMPTY = 32, BA_FULL = 64, BA_EMPTY = 80, BM_FULL = 96, BM_EMPTY = 112,
-                     BC_FULL = 128, BC_EMPTY = 136, B_TMEMPTR = 144, BR_FULL = 160, BR_EMPTY = 192;
+  // mbarriers (8 B each):  b_full[4] @0  b_empty[4] @32  a_full[4] @64  a_empty[4] @96
+  //                        main_full[2] @128  main_empty[2] @144 ; tmem ptr @160 ; raw_full[4] @192  raw_empty[4] @224
+  constexpr uint32_t BB_FULL = 0, BB_EMPTY = 32, BA_FULL = 64, BA_EMPTY = 96, BM_FULL = 128, BM_EMPTY = 144,
+                     B_TMEMPTR = 160, BR_FULL = 192, BR_EMPTY = 224;
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + TC_OFF_BAR + B_TMEMPTR);
   constexpr uint32_t NMAIN = TC_NMAIN;
-  constexpr uint32_t CORR_COL = TC_CORR_COL;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -387,8 +393,6 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       mbar_init(bar0 + BR_FULL + 8 * r, 1);     // raw A slot: expect_tx arrive + TMA bytes
       mbar_init(bar0 + BR_EMPTY + 8 * r, 4);    // 4 A-producer warps have read it
     }
-    mbar_init(bar0 + BC_FULL, 1);
-    mbar_init(bar0 + BC_EMPTY, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) tmem_alloc(sbase + TC_OFF_BAR + B_TMEMPTR, 512);
@@ -687,16 +691,11 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       int bs = 0, as = 0;
       uint32_t bphase = 0, aphase = 0;
       uint32_t mcount = 0;                 // main buffers handed out so far
-      uint32_t tphase = 0;                 // tile parity (corr buffer)
       long long tM[5] = {0, 0, 0, 0, 0};
-      // The tensor pipe takes one tcgen05.mma at a time from this thread (issuing 12 of them costs
-      // their execution time), so anything else the thread does leaves the pipe idle.  The
-      // readiness probes of the NEXT chunk (~70 cycles each) are therefore launched between the
-      // MMAs of the current one and only consumed at the top of the next iteration.
+      // The readiness probes of the NEXT chunk (~70 cycles each) are launched right after the MMAs of the
+      // current one have been queued and only consumed at the top of the next iteration.
       bool pre_a = false, pre_b = false, pre_m = false;
       for (int tile = cid; tile < total_tiles; tile += ncl) {
-        mbar_wait(bar0 + BC_EMPTY, tphase ^ 1);  // corr buffer drained by the epilogue of the previous tile
-        const uint32_t d_corr = tmem_base + CORR_COL;
         for (int c = 0; c < nchunks; ++c) {
           const uint32_t mb = mcount % NMAIN;
           const int cg = c % TC_FLUSH;                    // position in the flush group
@@ -719,30 +718,32 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           const int as_n = (as + 1 == TC_ASTAGES) ? 0 : as + 1, bs_n = (bs + 1 == TC_BSTAGES) ? 0 : bs + 1;
           const uint32_t aph_n = (as + 1 == TC_ASTAGES) ? (aphase ^ 1) : aphase;
           const uint32_t bph_n = (bs + 1 == TC_BSTAGES) ? (bphase ^ 1) : bphase;
+          // ONE elected block per chunk: every elect.sync + reconvergence costs ~50 cycles of this thread, and the
+          // thread's instruction stream, not the tensor pipe, paces the chunk rate (8 MMAs execute in ~500 cycles,
+          // the loop body took ~700 with one elected block per k-step: profiles/r02_tc_attribution.md).  The probes
+          // of the next chunk's barriers follow in the shadow of the MMAs just queued.
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) {
-            if (elect_one()) {
+            for (int k = 0; k < TC_BK / 8; ++k) {
               const uint64_t adv = (uint64_t)(k * 2);      // 8 fp32 = 32 B = 2 x 16 B
               if (DBG != 7) umma_tf32_ts(d_main, a_hi + 8 * k, b_hi + adv, TC_IDESC, (cg | k) ? 1u : 0u);
               // correction: bf16 k-step k of the K=64 row [A_lo | A_hi] . [B_hi | B_lo]^T (8 columns of bf16
               // pairs in tensor memory, 32 bytes of the swizzled B row, like a tf32 k-step).  (Issuing the four
               // tf32 MMAs first and the four bf16 ones after them measured 5 % slower than interleaving them.)
-              if (DBG != 3) umma_bf16_ts(d_corr, a_pk + 8 * k, b_pk + adv, TC_IDESC_BF, (c | k) ? 1u : 0u);
-              if (k == TC_BK / 8 - 1) {
-                if (TC_CLUSTER > 1) umma_commit_mc(bar0 + BB_EMPTY + 8 * bs, (uint16_t)((1u << TC_CLUSTER) - 1));
-                else umma_commit(bar0 + BB_EMPTY + 8 * bs);     // frees the B smem stage when the MMAs retire
-                umma_commit(bar0 + BA_EMPTY + 8 * as);          // frees the A tmem stage
-                if (last_of_group) umma_commit(bar0 + BM_FULL + 8 * mb);   // group sum ready
-              }
+              if (DBG != 3) umma_bf16_ts(d_main, a_pk + 8 * k, b_pk + adv, TC_IDESC_BF, (DBG == 7 && !(cg | k)) ? 0u : 1u);
             }
-            __syncwarp();
-            if (k == TC_PROBE_K) pre_a = mbar_try(bar0 + BA_FULL + 8 * as_n, aph_n);
-            if (k == TC_PROBE_K + (TC_PROBE_K < 3 ? 1 : 0)) pre_b = mbar_try(bar0 + BB_FULL + 8 * bs_n, bph_n);
+            if (TC_CLUSTER > 1) umma_commit_mc(bar0 + BB_EMPTY + 8 * bs, (uint16_t)((1u << TC_CLUSTER) - 1));
+            else umma_commit(bar0 + BB_EMPTY + 8 * bs);     // frees the B smem stage when the MMAs retire
+            umma_commit(bar0 + BA_EMPTY + 8 * as);          // frees the A tmem stage
+            if (last_of_group) umma_commit(bar0 + BM_FULL + 8 * mb);   // group sum ready
           }
+          __syncwarp();
+          pre_a = mbar_try(bar0 + BA_FULL + 8 * as_n, aph_n);
+          pre_b = mbar_try(bar0 + BB_FULL + 8 * bs_n, bph_n);
           if (last_of_group) {
             ++mcount;
             // the next chunk opens a flush group: probe its accumulator buffer as well
-            if (TC_PROBE_K >= 3) pre_m = mbar_try(bar0 + BM_EMPTY + 8 * (mcount % NMAIN), ((mcount / NMAIN) & 1) ^ 1);
+            pre_m = mbar_try(bar0 + BM_EMPTY + 8 * (mcount % NMAIN), ((mcount / NMAIN) & 1) ^ 1);
           }
           bs = bs_n; bphase = bph_n;
           as = as_n; aphase = aph_n;
@@ -751,9 +752,6 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
             tM[0] += 1; tM[1] += t1 - t0; tM[2] += t2 - t1; tM[3] += t3 - t2; tM[4] += t4 - t3;
           }
         }
-        if (elect_one()) umma_commit(bar0 + BC_FULL);       // correction term ready
-        __syncwarp();
-        tphase ^= 1;
       }
       if (DBG == 6 && p.dbg && lane == 0)
         for (int i = 0; i < 5; ++i) p.dbg[(size_t)blockIdx.x * 32 + 16 + i] = (unsigned long long)tM[i];
@@ -774,7 +772,6 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     const int fb = fr * J;                   // first row of this thread's frame
     const uint32_t ebar = 1u + (uint32_t)eh; // named barrier of this group
     uint32_t mcount = 0;
-    uint32_t tphase = 0;
     long long tE_n = 0, tE_wait = 0, tE_tot = clock64(), tE_tiles = 0, tE_cw = 0, tE_cl = 0, tE_fl = 0;
     const uint32_t lane_off = ((uint32_t)(ew * 32) << 16) + (uint32_t)(eh * TC_EN);
     float* scratch = staging;                // TC_EPI_BYTES, laid out per epilogue kind below
@@ -894,31 +891,6 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         if (lane == 0) mbar_arrive(bar0 + BM_EMPTY + 8 * mb);
         ++mcount;
       }
-      long long tc0 = 0;
-      if (DBG == 6) tc0 = clock64();
-      {
-        mbar_wait(bar0 + BC_FULL, tphase);
-        if (DBG == 6) { long long t1 = clock64(); tE_cw += t1 - tc0; tc0 = t1; }
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + CORR_COL + lane_off;
-        if (!noflush) {
-          uint32_t va[32], vb[32];
-          tmem_ld32_async(taddr, va);
-          tmem_ld32_async(taddr + 32, vb);
-          tmem_wait_ld(va);
-          tmem_wait_ld(vb);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            acc[i] += __uint_as_float(va[i]);
-            acc[32 + i] += __uint_as_float(vb[i]);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar0 + BC_EMPTY);
-        if (DBG == 6) { long long t1 = clock64(); tE_cl += t1 - tc0; tc0 = t1; }
-      }
-      tphase ^= 1;
       if (DBG == 6) ++tE_tiles;
 
       if (EPI == EPI_PLAIN) {
@@ -1173,8 +1145,8 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
 // host side
 // ----------------------------------------------------------------------------------------
 // Residual truncation bias of the in-TMEM accumulation of one flush group (measured -8.7e-8 relative
-// per 4 MMAs, tools/tc_probe.py): the partial sum after every k-step is truncated by ~0.5 ulp towards
-// zero, i.e. the product of k-step s is under-counted by TC_TRUNC_C * (steps left in its group).
+// per 4 MMAs, tools/tc_probe.py): the partial sum after every MMA is truncated by ~0.5 ulp towards
+// zero, i.e. the product of MMA s is under-counted by TC_TRUNC_C * (MMAs left in its group).
 // It is added back through the correction accumulator by folding it into W_lo (it is <= 2^-20 of W,
 // within W_lo's own rounding budget).
 constexpr float TC_TRUNC_C = 3.5e-8f;
@@ -1201,8 +1173,10 @@ __global__ void tc_split_kernel(const float* __restrict__ w, float* __restrict__
   const int nchunks = K / TC_BK;
   const int c = k / TC_BK, g = c / TC_FLUSH;
   const int glen = min(TC_FLUSH, nchunks - g * TC_FLUSH);            // chunks in this flush group
-  const int s = (c - g * TC_FLUSH) * (TC_BK / 8) + (k % TC_BK) / 8;  // k-step index inside the group
-  const float steps_left = (float)(glen * (TC_BK / 8) - s);          // truncations this product still sees
+  // MMA index of this product inside its flush group: a chunk issues 8 MMAs into the group's accumulator, in the
+  // order main(k-step 0), correction(0), main(1), correction(1), ...; every one of them truncates the accumulator
+  const int s = (c - g * TC_FLUSH) * (2 * TC_BK / 8) + 2 * ((k % TC_BK) / 8);
+  const float steps_left = (float)(glen * (2 * TC_BK / 8) - s);      // truncations this product still sees
   hi[i] = h;
   const float lo = (x - h) + TC_TRUNC_C * steps_left * h;
   unsigned short* prow = pk + row * 2 * K + (long long)c * 2 * TC_BK + (k - c * TC_BK);

@@ -112,7 +112,7 @@ static int bn_fwd(TCtx& c, BnSave& s, const std::string& prefix, const float* Z,
   col_stats_kernel<<<grid, 256, 0, c.st>>>(Z, M, N, ldz, sums, sums + N);
   bn_finalize_kernel<<<cdiv(N, 128), 128, 0, c.st>>>(sums, sums + N, M, N, s.mean, s.invstd, rm, rv, 0.1f);
   if (keep) {
-    dropout_mask_kernel<<<cdiv(M * N, 256), 256, 0, c.st>>>(keep, M * N, drop_p, ts.seed + 0x51ED270B * (++ts.drop_ctr));
+    dropout_mask_kernel<<<cdiv(M * N, 256), 256, 0, c.st>>>(keep, M * N, drop_p, ts.seed + 0x51ED270B * (++ts.drop_ctr), c.h->dropout_state);
   }
   bn_apply_kernel<<<cdiv(M * N, 256), 256, 0, c.st>>>(Z, ldz, s.mean, s.invstd, s.gamma, s.beta, relu, res, ldres, rmap,
                                                     c.J, keep, s.kscale, Y, ldy, M, N);

@@ -330,14 +330,20 @@ __global__ void copy2d_kernel(const float* __restrict__ src, int lds, float* __r
 
 // counter-based dropout mask (nn.Dropout semantics: keep with prob 1-p, scale 1/(1-p)); the
 // stream is ours, not torch's -- loss-match tests use p = 0 (SURVEY.md §7 "Dropout parity")
-__global__ void dropout_mask_kernel(unsigned char* __restrict__ keep, long long n, float p, unsigned long long seed) {
+// `dseed` (device, may be null): added to the seed, so that a CUDA-graph replay of the step -- whose kernel arguments
+// are frozen -- still draws a fresh mask (dropout_bump_kernel advances it once per forward).
+__global__ void dropout_mask_kernel(unsigned char* __restrict__ keep, long long n, float p, unsigned long long seed,
+                                    const unsigned long long* __restrict__ dseed) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (dseed) seed += *dseed;
   unsigned long long x = (unsigned long long)i * 0x9E3779B97F4A7C15ull + seed;
   x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
   float u = (float)(x >> 40) * (1.0f / 16777216.0f);
   keep[i] = (u >= p) ? 1 : 0;
 }
+
+__global__ void dropout_bump_kernel(unsigned long long* dseed) { *dseed += 0xD1B54A32D192ED03ull; }
 
 // ----------------------------------------------------------------------------------------------
 // SemCH joint mixing and its adjoints (model/local_attention.py:35-53)

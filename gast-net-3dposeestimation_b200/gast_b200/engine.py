@@ -233,6 +233,10 @@ class _TrainFn(torch.autograd.Function):
             y = torch.empty((B, T_out, module.num_joints_in, 3), dtype=torch.float32, device=dev)
             p = float(module._gast_dropout)
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
+            # device-side dropout counter (set by a graph-capturing trainer): keeps the masks fresh across replays
+            ds = module.__dict__.get('_gast_dropout_state')
+            _check(lib.gast_set_dropout_state(handle.h, C.c_void_p(ds.data_ptr() if ds is not None else None)),
+                   'gast_set_dropout_state')
             _check(lib.gast_forward_train(handle.h, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), B, T,
                                           C.c_float(p), C.c_uint64(seed), C.c_void_p(ws.data_ptr()), ws.numel(),
                                           C.c_void_p(st)), 'gast_forward_train')

@@ -141,6 +141,10 @@ size_t gast_train_workspace_bytes(gast_t* h, int32_t B, int32_t T, float dropout
 int gast_forward_train(gast_t* h, const float* x, float* y, int32_t B, int32_t T, float dropout_p, uint64_t seed,
                        void* workspace, size_t workspace_bytes, void* stream);
 int gast_backward(gast_t* h, const float* dy, void* workspace, size_t workspace_bytes, void* stream);
+/* Optional device-side dropout state: one uint64 on the device (caller-owned, may be null to unset) that is added to
+ * `seed` by every dropout kernel and advanced once per gast_forward_train.  With it a CUDA graph that captured a
+ * training step (frozen kernel arguments) draws a fresh mask at every replay. */
+int gast_set_dropout_state(gast_t* h, void* dev_u64);
 
 /* ---- real-time causal streams (gen_skes.py:43-69, tools/inference.py:19-110) -------------
  * The reference's real-time model is a causal SpatioTemporalModelOptimized1f re-run on the last

@@ -311,3 +311,38 @@ def test_fused_adam_invalidates_bn_free_submodule_constants():
     with torch.no_grad():
         y1 = sc(x)
     assert (y1 - y0).abs().max().item() > 1e-3
+
+
+def test_graphed_trainer_matches_eager_steps():
+    """the CUDA-graph replay of forward + loss + backward (gast_b200.trainer.GraphedTrainer) against the eager step:
+    same kernels, same order -> same parameters after three Adam(amsgrad) steps (dropout 0); with dropout the replayed
+    masks differ from step to step (device-side dropout counter)."""
+    from model.gast_net import SpatioTemporalModelOptimized1f
+    from gast_b200.trainer import DataParallelTrainer, GraphedTrainer
+    from gast_b200.pipeline import FusedAdam
+
+    def make(drop):
+        m = SpatioTemporalModelOptimized1f(_adj(17), 17, 2, 17, [3, 3, 3], dropout=drop, channels=32)
+        synth.randomize_module(m, 3)
+        return m.cuda()
+    opt = lambda ps: FusedAdam(ps, lr=1e-3, amsgrad=True)
+    B = 16
+    xs = [torch.from_numpy(synth.synth_input(B, 27, 17, 2, seed=40 + i)).cuda() for i in range(3)]
+    ys = [torch.from_numpy(synth.synth_target(B, 17, seed=50 + i)).cuda() for i in range(3)]
+    a = DataParallelTrainer(make(0.0), opt)
+    b = GraphedTrainer(make(0.0), opt, (B, 27, 17, 2), (B, 1, 17, 3))
+    b.model.load_state_dict(a.model.state_dict())          # (warm-up steps of the graph trainer touch only gradients / BN stats)
+    for x, y in zip(xs, ys):
+        la = a.step(x, y)
+        lb = b.step(x, y)
+        assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(la))
+    for (k, p), (_, q) in zip(a.model.named_parameters(), b.model.named_parameters()):
+        assert torch.allclose(p, q, rtol=0, atol=1e-6), k
+    c = GraphedTrainer(make(0.25), opt, (B, 27, 17, 2), (B, 1, 17, 3))
+    l1 = float(c.step(xs[0], ys[0]))
+    w = [p.detach().clone() for p in c.model.parameters()]
+    c.graph.replay()
+    g1 = c.flat.flat.clone()
+    c.graph.replay()
+    assert not torch.equal(g1, c.flat.flat)               # a new dropout mask at every replay
+    assert l1 > 0 and all(torch.isfinite(p).all() for p in w)
