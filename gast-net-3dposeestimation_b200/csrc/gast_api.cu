@@ -391,7 +391,7 @@ static int prepare_global(gast_handle* h, Lookup& L, cudaStream_t st, BlockConst
     CUDA_OK(cudaMemcpyAsync(b.Wg + (size_t)hd * Cg * C, gw, sizeof(float) * Cg * C, cudaMemcpyDeviceToDevice, st));
     CUDA_OK(cudaMemcpyAsync(b.bg + (size_t)hd * Cg, gb, sizeof(float) * Cg, cudaMemcpyDeviceToDevice, st));
     CUDA_OK(cudaMemcpyAsync(b.Ck + (size_t)hd * J * J, ck, sizeof(float) * J * J, cudaMemcpyDeviceToDevice, st));
-    global_collapse_kernel<<<cdiv(C, 128), 128, 0, st>>>(b.U, b.cab, tw, tb, pw, pb, wc, hd, C, Ci);
+    global_collapse_kernel<<<cdiv(C, 32), 256, 0, st>>>(b.U, b.cab, tw, tb, pw, pb, wc, hd, C, Ci);
   }
   if (kind != GAST_KIND_GLOBAL_HEAD) {
     const float* w = L.get(gp + "cat_conv.weight", (int64_t)C * C);

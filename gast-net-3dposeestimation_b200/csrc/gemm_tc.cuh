@@ -89,6 +89,14 @@ static_assert(TC_REG_A + 2 * TC_REG_E + TC_REG_M <= 512, "register file over-sub
 #endif
 constexpr int TC_CONV_PIPE = GAST_TC_CONV_PIPE;
 
+// MMA issue: 1 = two issuing warps (9 and 11) take alternate flush groups (each owns one accumulator buffer and its
+// own set of operand "full" barriers), 0 = warp 9 issues everything
+#ifndef GAST_TC_DUAL_ISSUE
+#define GAST_TC_DUAL_ISSUE 0
+#endif
+constexpr int TC_DUAL_ISSUE = GAST_TC_DUAL_ISSUE;
+constexpr int TC_NISSUE = TC_DUAL_ISSUE ? 2 : 1;
+
 
 constexpr int TC_EN = 64;         // accumulator columns owned by one epilogue warpgroup
 constexpr int TC_STAGE_BYTES = 2 * 16384;            // B_hi, B_lo : 128 rows x 128 B each
@@ -107,7 +115,7 @@ constexpr int TC_OFF_AB = TC_OFF_STAGING + TC_EPI_BYTES;
 constexpr int TC_OFF_XPOSE = (TC_OFF_AB + 128 * 8 * 4 + 1023) / 1024 * 1024;  // raw A ring (1024-aligned: TMA SWIZZLE_128B)
 constexpr int TC_OFF_BAR = TC_OFF_XPOSE + TC_RSTAGES * 128 * TC_XLD * 4;
 static_assert(TC_OFF_STAGING % 1024 == 0 && TC_OFF_XPOSE % 1024 == 0, "swizzled regions must be 1024-byte aligned");
-constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 256 + 1024;
+constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 384 + 1024;
 static_assert(TC_SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");   // 26 mbarriers + tmem ptr, + alignment slack
 
 // ----------------------------------------------------------------------------------------
@@ -328,6 +336,17 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(T
 constexpr uint32_t TC_IDESC_BF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
                                  ((uint32_t)(TC_BM >> 4) << 24);
 
+// issuer of the flush group a chunk belongs to: groups are numbered over all tiles of a CTA
+struct TcGroupOf {
+  int ct = 0; uint32_t grp = 0;
+  __device__ __forceinline__ int role() const { return (int)(grp % TC_NISSUE); }
+  __device__ __forceinline__ void next(int nchunks_) {
+    ++ct;
+    if (ct == nchunks_) { ct = 0; ++grp; }
+    else if ((ct % TC_FLUSH) == 0) ++grp;
+  }
+};
+
 // ----------------------------------------------------------------------------------------
 // kernel
 // ----------------------------------------------------------------------------------------
@@ -357,10 +376,13 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
   float* staging = reinterpret_cast<float*>(smem + TC_OFF_STAGING);
   float* ab_s = reinterpret_cast<float*>(smem + TC_OFF_AB);
   const uint32_t bar0 = sbase + TC_OFF_BAR;
-  // mbarriers (8 B each):  b_full[4] @0  b_empty[4] @32  a_full[4] @64  a_empty[4] @96
-  //                        main_full[2] @128  main_empty[2] @144 ; tmem ptr @160 ; raw_full[4] @192  raw_empty[4] @224
-  constexpr uint32_t BB_FULL = 0, BB_EMPTY = 32, BA_FULL = 64, BA_EMPTY = 96, BM_FULL = 128, BM_EMPTY = 144,
-                     B_TMEMPTR = 160, BR_FULL = 192, BR_EMPTY = 224;
+  // mbarriers (8 B each):  b_full[4 stages][2 issuers] @0  b_empty[4] @64  a_full[4][2] @96  a_empty[4] @160
+  //                        main_full[2] @192  main_empty[2] @208 ; tmem ptr @224 ; raw_full[4] @256  raw_empty[4] @288
+  // The operand "full" barriers exist once per issuing warp: the issuer of a chunk's flush group is the only
+  // waiter of that barrier instance, so it sees EVERY phase of it (an mbarrier parity wait cannot tell a phase
+  // from the one two later, which an issuer that skips the other issuer's chunks would otherwise run into).
+  constexpr uint32_t BB_FULL = 0, BB_EMPTY = 64, BA_FULL = 96, BA_EMPTY = 160, BM_FULL = 192, BM_EMPTY = 208,
+                     B_TMEMPTR = 224, BR_FULL = 256, BR_EMPTY = 288;
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + TC_OFF_BAR + B_TMEMPTR);
   constexpr uint32_t NMAIN = TC_NMAIN;
 
@@ -378,11 +400,11 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
 
   if (tid == 0) {
     for (int s = 0; s < TC_BSTAGES; ++s) {
-      mbar_init(bar0 + BB_FULL + 8 * s, 1);     // expect_tx arrive + TMA bytes
+      for (int q = 0; q < 2; ++q) mbar_init(bar0 + BB_FULL + 8 * (2 * s + q), 1);     // expect_tx arrive + TMA bytes
       mbar_init(bar0 + BB_EMPTY + 8 * s, TC_CLUSTER);   // tcgen05.commit of every CTA of the cluster
     }
     for (int s = 0; s < TC_ASTAGES; ++s) {
-      mbar_init(bar0 + BA_FULL + 8 * s, 4);     // 4 A-producer warps
+      for (int q = 0; q < 2; ++q) mbar_init(bar0 + BA_FULL + 8 * (2 * s + q), 4);     // 4 A-producer warps
       mbar_init(bar0 + BA_EMPTY + 8 * s, 1);    // tcgen05.commit
     }
     for (int b = 0; b < (int)NMAIN; ++b) {
@@ -493,19 +515,21 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     const int my_row = warp * 32 + lane;
     const bool row_in_box = my_row < p.fpt * J;
     // raw rows of one chunk -> 8 float4 of this thread's row (swizzle-aware, conflict-free)
+    // (rows of the tile that the TMA box does not cover -- 119..127 for J = 17 -- are never written by the TMA:
+    //  their owners zero them once in every raw slot instead of masking 32 values per chunk)
     auto load_raw = [&](int slot_, float4 (&xr)[8]) {
       const float* rowp = reinterpret_cast<const float*>(smem + TC_OFF_XPOSE + slot_ * 16384 + my_row * 128);
       const int sw = my_row & 7;              // TMA SWIZZLE_128B: 16-byte chunk index ^= row % 8
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        xr[i] = *reinterpret_cast<const float4*>(rowp + ((i ^ sw) << 2));
-        if (!row_in_box) xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // rows the box does not cover
-      }
+      for (int i = 0; i < 8; ++i) xr[i] = *reinterpret_cast<const float4*>(rowp + ((i ^ sw) << 2));
     };
     auto split_row = [&](const float4 (&xr)[8], uint32_t* hi, uint32_t* lo) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 x = xr[i];
+        // (splitting by TRUNCATION -- the raw value as the tf32 operand, x - trunc(x) as the correction -- saves an
+        //  integer op per element but measured no faster and doubles the error of the bf16 correction:
+        //  profiles/r02_tc_attribution.md, experiment 11)
         const float h0 = tf32_rn_fast(x.x), h1 = tf32_rn_fast(x.y), h2 = tf32_rn_fast(x.z), h3 = tf32_rn_fast(x.w);
         hi[4 * i + 0] = __float_as_uint(h0); hi[4 * i + 1] = __float_as_uint(h1);
         hi[4 * i + 2] = __float_as_uint(h2); hi[4 * i + 3] = __float_as_uint(h3);
@@ -515,8 +539,17 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         lo[16 + 2 * i + 1] = pack_bf16x2(h2, h3);
       }
     };
+    TcGroupOf gof;                            // which issuer waits for the chunk being converted
     if (atma && TC_CONV_PIPE && DBG == 0) {
       float4 xr[8];
+      if (!row_in_box) {
+#pragma unroll
+        for (int sl = 0; sl < TC_RSTAGES; ++sl) {
+          float4* rz = reinterpret_cast<float4*>(smem + TC_OFF_XPOSE + sl * 16384 + my_row * 128);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       if (my_chunks > 0) {
         mbar_wait(bar0 + BR_FULL + 8 * slot, rphase);
         load_raw(slot, xr);
@@ -539,7 +572,8 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar0 + BA_FULL + 8 * stage);
+        if (lane == 0) mbar_arrive(bar0 + BA_FULL + 8 * (2 * stage + gof.role()));
+        gof.next(nchunks);
         if (++stage == TC_ASTAGES) { stage = 0; phase ^= 1; }
       }
     } else
@@ -596,7 +630,8 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar0 + BA_FULL + 8 * stage);
+      if (lane == 0) mbar_arrive(bar0 + BA_FULL + 8 * (2 * stage + gof.role()));
+      gof.next(nchunks);
       if (DBG == 6) tA_st += clock64() - t0;
       if (++stage == TC_ASTAGES) { stage = 0; phase ^= 1; }
       if (++slot == TC_RSTAGES) { slot = 0; rphase ^= 1; }
@@ -616,14 +651,15 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       int stage = 0;
       uint32_t phase = 0;
       long long tB_wait = 0;
+      TcGroupOf gof;
       for (int tile = cid; tile < total_tiles; tile += ncl) {
         const int n0 = (tile % n_tiles_n) * TC_BN;
-        for (int c = 0; c < nchunks; ++c) {
+        for (int c = 0; c < nchunks; ++c, gof.next(nchunks)) {
           long long t0 = 0;
           if (DBG == 6) t0 = clock64();
           mbar_wait(bar0 + BB_EMPTY + 8 * stage, phase ^ 1);     // every CTA of the cluster consumed it
           if (DBG == 6) tB_wait += clock64() - t0;
-          const uint32_t full = bar0 + BB_FULL + 8 * stage;
+          const uint32_t full = bar0 + BB_FULL + 8 * (2 * stage + gof.role());
           if (DBG == 8 || DBG == 9) {                            // experiment: MMAs on stale smem, no B traffic
             mbar_arrive(full);
             if (++stage == TC_BSTAGES) { stage = 0; phase ^= 1; }
@@ -681,6 +717,77 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       }
     }
     __syncwarp();
+    } else if (TC_DUAL_ISSUE && (warp == 9 || warp == 11)) {
+    // ================================================================= MMA issuers (two)
+    // The 8 MMAs of a chunk execute in ~500 cycles, but one thread needs ~620 cycles per chunk for the barrier
+    // checks, descriptors, commits and probes around them ("MMAs + barrier hand-shakes only" ran at 0.68 ms where
+    // the tensor pipe needs 0.41 ms, profiles/r02_tc_attribution.md): the issuing thread paces the kernel.  So
+    // warp 9 issues the even flush groups and warp 11 the odd ones.  A flush group has its own accumulator buffer
+    // (group g -> buffer g % 2), so issuer `role` owns buffer `role` and no ordering between the two threads' MMAs
+    // is needed; operand stages are consumed in ring order, each released by the commit of the thread that used
+    // it, and each issuer waits on its OWN instance of the operand "full" barriers (see the barrier table).
+    {
+      const int role = (warp == 11) ? 1 : 0;
+      int bs = 0, as = 0;                  // ring positions of the next chunk in global order (both issuers' chunks)
+      uint32_t aph = 0, bph = 0;           // bit s: parity this issuer waits for next on its barrier of stage s
+      uint32_t gcount = 0;                 // flush groups so far (both issuers')
+      long long tM[5] = {0, 0, 0, 0, 0};
+      bool pre_a = false, pre_b = false;
+      for (int tile = cid; tile < total_tiles; tile += ncl) {
+        for (int c0 = 0; c0 < nchunks; c0 += TC_FLUSH, ++gcount) {
+          const int glen = min(TC_FLUSH, nchunks - c0);
+          if ((int)(gcount % TC_NISSUE) != role) {        // the other issuer's group: step over its chunks
+            as = (as + glen) % TC_ASTAGES;
+            bs = (bs + glen) % TC_BSTAGES;
+            continue;
+          }
+          const uint32_t mb = gcount % NMAIN;
+          mbar_wait(bar0 + BM_EMPTY + 8 * mb, ((gcount / NMAIN) & 1) ^ 1);   // the epilogue has drained this buffer
+          const uint32_t d_main = tmem_base + mb * TC_BN;
+          for (int cg = 0; cg < glen; ++cg) {
+            long long t0 = 0, t2 = 0, t3 = 0;
+            if (DBG == 6) t0 = clock64();
+            if (!pre_a) mbar_wait(bar0 + BA_FULL + 8 * (2 * as + role), (aph >> as) & 1u);
+            if (DBG == 6) t2 = clock64();
+            if (!pre_b) mbar_wait(bar0 + BB_FULL + 8 * (2 * bs + role), (bph >> bs) & 1u);
+            if (DBG == 6) t3 = clock64();
+            aph ^= 1u << as; bph ^= 1u << bs;
+            tc_fence_after();
+            const uint32_t a_hi = tmem_base + TC_A_COL + as * 64, a_pk = a_hi + 32;
+            const uint32_t sb = sbase + bs * TC_STAGE_BYTES;
+            const uint64_t b_hi = make_smem_desc(sb), b_pk = make_smem_desc(sb + 16384);
+            const bool last_of_group = (cg == glen - 1);
+            const int as_n = (as + 1 == TC_ASTAGES) ? 0 : as + 1, bs_n = (bs + 1 == TC_BSTAGES) ? 0 : bs + 1;
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < TC_BK / 8; ++k) {
+                const uint64_t adv = (uint64_t)(k * 2);      // 8 fp32 = 32 B = 2 x 16 B
+                if (DBG != 7) umma_tf32_ts(d_main, a_hi + 8 * k, b_hi + adv, TC_IDESC, (cg | k) ? 1u : 0u);
+                if (DBG != 3) umma_bf16_ts(d_main, a_pk + 8 * k, b_pk + adv, TC_IDESC_BF, (DBG == 7 && !(cg | k)) ? 0u : 1u);
+              }
+              if (TC_CLUSTER > 1) umma_commit_mc(bar0 + BB_EMPTY + 8 * bs, (uint16_t)((1u << TC_CLUSTER) - 1));
+              else umma_commit(bar0 + BB_EMPTY + 8 * bs);     // frees the B smem stage when the MMAs retire
+              umma_commit(bar0 + BA_EMPTY + 8 * as);          // frees the A tmem stage
+              if (last_of_group) umma_commit(bar0 + BM_FULL + 8 * mb);   // group sum ready
+            }
+            __syncwarp();
+            if (!last_of_group) {          // (after a group this issuer's next chunk is a whole group away)
+              pre_a = mbar_try(bar0 + BA_FULL + 8 * (2 * as_n + role), (aph >> as_n) & 1u);
+              pre_b = mbar_try(bar0 + BB_FULL + 8 * (2 * bs_n + role), (bph >> bs_n) & 1u);
+            } else {
+              pre_a = pre_b = false;
+            }
+            as = as_n; bs = bs_n;
+            if (DBG == 6) {
+              const long long t4 = clock64();
+              tM[0] += 1; tM[2] += t2 - t0; tM[3] += t3 - t2; tM[4] += t4 - t3;
+            }
+          }
+        }
+      }
+      if (DBG == 6 && p.dbg && lane == 0 && role == 0)
+        for (int i = 0; i < 5; ++i) p.dbg[(size_t)blockIdx.x * 32 + 16 + i] = (unsigned long long)tM[i];
+    }
     } else if (warp == 9) {
     // ================================================================= MMA issuer
     // The whole warp runs this loop converged so that descriptors and barrier addresses live in
@@ -704,9 +811,9 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           if (cg == 0 && !pre_m) mbar_wait(bar0 + BM_EMPTY + 8 * mb, ((mcount / NMAIN) & 1) ^ 1);
           pre_m = false;
           if (DBG == 6) t1 = clock64();
-          if (!pre_a) mbar_wait(bar0 + BA_FULL + 8 * as, aphase);
+          if (!pre_a) mbar_wait(bar0 + BA_FULL + 16 * as, aphase);
           if (DBG == 6) t2 = clock64();
-          if (!pre_b) mbar_wait(bar0 + BB_FULL + 8 * bs, bphase);
+          if (!pre_b) mbar_wait(bar0 + BB_FULL + 16 * bs, bphase);
           if (DBG == 6) t3 = clock64();
           tc_fence_after();
           const uint32_t d_main = tmem_base + mb * TC_BN;
@@ -738,8 +845,8 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
             if (last_of_group) umma_commit(bar0 + BM_FULL + 8 * mb);   // group sum ready
           }
           __syncwarp();
-          pre_a = mbar_try(bar0 + BA_FULL + 8 * as_n, aph_n);
-          pre_b = mbar_try(bar0 + BB_FULL + 8 * bs_n, bph_n);
+          pre_a = mbar_try(bar0 + BA_FULL + 16 * as_n, aph_n);
+          pre_b = mbar_try(bar0 + BB_FULL + 16 * bs_n, bph_n);
           if (last_of_group) {
             ++mcount;
             // the next chunk opens a flush group: probe its accumulator buffer as well

@@ -272,8 +272,10 @@ static int block_bwd(TCtx& c, BlockSave& b, BlockConsts& bc, const float* dOut, 
   }
   if (dense_tn(c, dG, C, b.X, C, M, C, C, dWg, C)) return 1;
   if (dense_nn(c, dG, C, bc.Wg, C, M, C, C, dXg, C)) return 1;
+  // dU[8][C] = dab[M][8]^T . X[M][C]: the same row-contraction as a weight gradient (a one-thread-per-output
+  // kernel took 3.4 ms per block at b = 128)
+  if (dense_tn(c, dab, 8, b.X, C, M, 8, C, dU, C)) return 1;
   if (!c.dry) {
-    rowdot_bwd_u_kernel<<<cdiv((long long)8 * C, 128), 128, 0, c.st>>>(dab, b.X, C, 8, M, C, dU);
     rowdot_bwd_x_kernel<<<cdiv(M * C, 256), 256, 0, c.st>>>(dab, bc.U, 8, M, C, dXg, C);
     add_inplace_kernel<<<cdiv(M * C, 256), 256, 0, c.st>>>(dX, dXg, M * C);
     const int Cg = C / 4;
@@ -297,7 +299,7 @@ static int block_bwd(TCtx& c, BlockSave& b, BlockConsts& bc, const float* dOut, 
       const float* pb = c.L->get(hp + "phi.bias", Cg);
       const float* wc = c.L->get(hp + "concat_project.0.weight", 2 * Cg);
       if (!c.L->ok) return 1;
-      global_collapse_bwd_kernel<<<cdiv(Cg, 64), 64, 0, c.st>>>(dU, dcab, hd, C, Cg, tw, tb, pw, pb, wc, gtw, gtb, gpw, gpb, gwc);
+      global_collapse_bwd_kernel<<<Cg, 128, 0, c.st>>>(dU, dcab, hd, C, Cg, tw, tb, pw, pb, wc, gtw, gtb, gpw, gpb, gwc);
     }
   }
   // (c) local branch
@@ -319,6 +321,8 @@ static int block_bwd(TCtx& c, BlockSave& b, BlockConsts& bc, const float* dOut, 
   float* dXl = c.fl((size_t)M * C);
   for (int m = 0; m < 2; ++m) {
     float* dA = c.fl((size_t)h->nnz[m] * C);
+    const int dsplit = (int)std::max<long long>(1, std::min<long long>(32, F / 32));   // frame ranges of semch_dcoef_kernel
+    double* dpart = c.dbl((size_t)dsplit * h->nnz[m] * C);
     if (c.dry) continue;
     const std::string g = lp + (m == 0 ? "gcn_sym." : "gcn_con.");
     float* ge = grad_ptr(h, g + "e", (int64_t)C * h->nnz[m]);
@@ -326,8 +330,9 @@ static int block_bwd(TCtx& c, BlockSave& b, BlockConsts& bc, const float* dOut, 
     NbrRows nr = nbr_rows(h->nbr[m], J);
     semch_mix_bwd_kernel<<<cdiv(M * C, 256), 256, 0, c.st>>>(dS + m * C, 2 * C, b.coefA[m], h->nbr[m], nr, h->nnz[m], J, F,
                                                             C, dH + m * 2 * C, 4 * C);
-    semch_dcoef_kernel<<<cdiv((long long)h->nnz[m] * C, 128), 128, 0, c.st>>>(dS + m * C, 2 * C, b.H + m * 2 * C, 4 * C,
-                                                                             h->nbr[m], nr, h->nnz[m], J, F, C, dA);
+    semch_dcoef_kernel<<<dim3(cdiv((long long)h->nnz[m] * C, 128), dsplit), 128, 0, c.st>>>(
+        dS + m * C, 2 * C, b.H + m * 2 * C, 4 * C, h->nbr[m], nr, h->nnz[m], J, F, C, dpart);
+    semch_dcoef_reduce_kernel<<<cdiv((long long)h->nnz[m] * C, 128), 128, 0, c.st>>>(dpart, dsplit, h->nnz[m] * C, dA);
     semch_de_kernel<<<cdiv((long long)C * J, 128), 128, 0, c.st>>>(b.coefA[m], dA, h->nbr[m], h->nnz[m], J, C, ge);
   }
   if (dense_tn(c, dH, 4 * C, b.X, C, M, 4 * C, C, dWst, C)) return 1;

@@ -394,15 +394,27 @@ __global__ void semch_mix_bwd_kernel(const float* __restrict__ dS, int lds, cons
 // dA[z][c] = sum_f dS[(f,row z),c] * H_w[(f,col z),c]     (thread per (z,c), loop over frames)
 __global__ void semch_dcoef_kernel(const float* __restrict__ dS, int lds, const float* __restrict__ H, int ldh,
                                    NbrTable nb, NbrRows nr, int nnz, int J, long long F, int C,
-                                   float* __restrict__ dA) {
+                                   double* __restrict__ part /* [gridDim.y][nnz*C] */) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nnz * C) return;
   int z = idx / C, c = idx - z * C;
   int i = nr.rowof[z], jn = nb.col[z];
   int off = (jn == i) ? 0 : C;
+  // frames split over gridDim.y (one thread per output summing every frame took 0.12 ms per mask at b = 128);
+  // the partial sums are added in split order by semch_dcoef_reduce_kernel: deterministic
+  const long long per = (F + gridDim.y - 1) / gridDim.y;
+  const long long f0 = (long long)blockIdx.y * per, f1 = min(F, f0 + per);
   double s = 0.0;
-  for (long long f = 0; f < F; ++f)
+  for (long long f = f0; f < f1; ++f)
     s += (double)dS[(f * J + i) * lds + c] * (double)H[(f * J + jn) * ldh + off + c];
+  part[(long long)blockIdx.y * nnz * C + idx] = s;
+}
+
+__global__ void semch_dcoef_reduce_kernel(const double* __restrict__ part, int S, int n, float* __restrict__ dA) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  double s = 0.0;
+  for (int i = 0; i < S; ++i) s += part[(long long)i * n + idx];
   dA[idx] = (float)s;
 }
 
@@ -562,21 +574,33 @@ __global__ void global_collapse_bwd_kernel(const float* __restrict__ dU, const f
                                            const float* __restrict__ wc, float* __restrict__ g_tw,
                                            float* __restrict__ g_tb, float* __restrict__ g_pw, float* __restrict__ g_pb,
                                            float* __restrict__ g_wc) {
-  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  // one block per inter-channel m, the C input channels over the threads (coalesced rows, block reduction)
+  const int m = blockIdx.x;
   if (m >= Ci) return;
   const float* du_t = dU + (long long)(2 * h) * C;
   const float* du_p = dU + (long long)(2 * h + 1) * C;
-  float dwt = tb[m] * dcab[2 * h], dwp = pb[m] * dcab[2 * h + 1];
-  for (int k = 0; k < C; ++k) {
-    g_tw[(long long)m * C + k] = wc[m] * du_t[k];
-    g_pw[(long long)m * C + k] = wc[Ci + m] * du_p[k];
-    dwt = fmaf(tw[(long long)m * C + k], du_t[k], dwt);
-    dwp = fmaf(pw[(long long)m * C + k], du_p[k], dwp);
+  const float wt = wc[m], wp = wc[Ci + m];
+  float dwt = 0.f, dwp = 0.f;
+  for (int k = threadIdx.x; k < C; k += blockDim.x) {
+    const float ut = du_t[k], up = du_p[k];
+    g_tw[(long long)m * C + k] = wt * ut;
+    g_pw[(long long)m * C + k] = wp * up;
+    dwt = fmaf(tw[(long long)m * C + k], ut, dwt);
+    dwp = fmaf(pw[(long long)m * C + k], up, dwp);
   }
-  g_tb[m] = wc[m] * dcab[2 * h];
-  g_pb[m] = wc[Ci + m] * dcab[2 * h + 1];
-  g_wc[m] = dwt;
-  g_wc[Ci + m] = dwp;
+  __shared__ float red[2][32];
+  dwt = warp_sum(dwt); dwp = warp_sum(dwp);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[0][w] = dwt; red[1][w] = dwp; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = tb[m] * dcab[2 * h], b = pb[m] * dcab[2 * h + 1];
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[0][i]; b += red[1][i]; }
+    g_tb[m] = wt * dcab[2 * h];
+    g_pb[m] = wp * dcab[2 * h + 1];
+    g_wc[m] = a;
+    g_wc[Ci + m] = b;
+  }
 }
 
 // shrink adjoints (N = 3): dX[m][k] = sum_o dy[m][o] Ws[o][k] ; dWs[o][k] = sum_m dy[m][o] X[m][k]
