@@ -96,6 +96,9 @@ struct gast_handle {
   int launches = 0;
   int tc_launches = 0;
   int gemm_core = 0;                 // 0 auto (tcgen05 where possible), 1 force FFMA
+  // training: per-GEMM tcgen05 operand copies (3xTF32), indexed by the GEMM's position in the step (train.cuh)
+  std::vector<TcWeights> train_tc;
+  bool train_tc_on = true;
   // optional per-launch device timing (bench.py roofline): event pairs around every launch
   bool timing = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -204,6 +207,7 @@ extern "C" int gast_create(gast_t** out, const gast_cfg* cfg) {
   h->cfg = *cfg;
   h->sm_count = prop.multiProcessorCount;
   h->fpt = 128 / J;
+  if (const char* e = getenv("GAST_TRAIN_TC")) h->train_tc_on = atoi(e) != 0;   // 0: training GEMMs on the FFMA core (A/B runs)
   h->sym_r.assign(cfg->sym_rows, cfg->sym_rows + cfg->sym_nnz);
   h->sym_c.assign(cfg->sym_cols, cfg->sym_cols + cfg->sym_nnz);
   h->nnz[0] = cfg->sym_nnz;
@@ -1003,6 +1007,7 @@ extern "C" int gast_backward(gast_t* h, const float* dy, void* workspace, size_t
   Arena a{reinterpret_cast<char*>(wsb), workspace_bytes, ts.arena_off, false};
   Lookup L{h};
   TCtx c{h, st, &a, &L, h->cfg.num_joints, false};
+  c.tc_slot = 1024;                         // the backward's GEMMs follow the forward's in the operand-copy table
   if (train_backward(h, c, ts, dy)) return 1;
   if (a.off > workspace_bytes) return fail("gast_backward: workspace overrun");
   CUDA_OK(cudaGetLastError());
@@ -1032,11 +1037,13 @@ extern "C" int gast_debug_gemm(const float* A, const float* W, float* out, int32
   std::vector<void*> owned;
   TcWeights t;
   int sms = 148;
+  const int prec = (core == 2) ? 1 : 0;     // core 2 = the tcgen05 core in 3xTF32 arithmetic (training)
+  if (core == 2) core = 0;
   if (core == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    rc = tc_prepare_weights(t, W, N, K, st, &owned);
+    rc = tc_prepare_weights(t, W, N, K, st, &owned, 0, prec);
     if (rc || !t.ready || !tc_supported(p, EPI_PLAIN, t)) {
       for (void* q : owned) cudaFree(q);
       return fail("gast_debug_gemm: shape not supported by the tcgen05 core (rc=%d)", rc);

@@ -49,6 +49,7 @@ struct TcWeights {
   float* lo = nullptr;   // the same bytes as [N][2K] bf16: per 32-wide K chunk [hi | lo] (correction operand)
   CUtensorMap map_hi, map_lo;
   int N = 0, K = 0;
+  int prec = 0;          // 0: `lo` holds the bf16 [hi | lo] rows; 1 (3xTF32, training): `lo` holds fp32 W - tf32(W), [N][K]
   bool ready = false;
 };
 
@@ -355,7 +356,13 @@ struct TcGroupOf {
 // 6 = full kernel + clock64() attribution of every role's waits (written to p.dbg[blockIdx.x*32 + i]),
 // 7 = correction (bf16) MMAs only, 8 = 5 + no B loads (MMAs on stale shared memory), 9 = 8 + A converters reduced to
 // their barrier hand-shakes (no shared-memory reads, no split): the floor of the MMA issue loop and the barrier protocol.
-template <int EPI, int DBG = 0>
+// PREC: 0 = one TF32 product + ONE bf16 correction product per chunk (inference: 2e-6 rms per GEMM); 1 = 3xTF32 --
+// both correction products A_lo.B_hi and A_hi.B_lo as kind::tf32 MMAs on fp32 `lo` operands (12 MMAs per chunk, 3e-7 rms:
+// as good as an fp32 FFMA GEMM).  The training path uses PREC = 1: its parity bar is the reference's own fp32 gradient
+// noise (tests/test_gpu_train.py), which the bf16 corrections would exceed.  Same rings, barriers and tensor-memory map:
+// the 32 "pair" columns of an A stage hold 32 fp32 lo values instead of 16 + 16 bf16 pairs, the second 16 KB of a B
+// stage the fp32 lo tile instead of the bf16 [hi | lo] rows.
+template <int EPI, int DBG = 0, int PREC = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap amap0,
@@ -533,10 +540,15 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         const float h0 = tf32_rn_fast(x.x), h1 = tf32_rn_fast(x.y), h2 = tf32_rn_fast(x.z), h3 = tf32_rn_fast(x.w);
         hi[4 * i + 0] = __float_as_uint(h0); hi[4 * i + 1] = __float_as_uint(h1);
         hi[4 * i + 2] = __float_as_uint(h2); hi[4 * i + 3] = __float_as_uint(h3);
-        lo[2 * i + 0] = pack_bf16x2(x.x - h0, x.y - h1);
-        lo[2 * i + 1] = pack_bf16x2(x.z - h2, x.w - h3);
-        lo[16 + 2 * i + 0] = pack_bf16x2(h0, h1);
-        lo[16 + 2 * i + 1] = pack_bf16x2(h2, h3);
+        if (PREC == 1) {                       // 3xTF32: the remainder as a tf32 operand of its own (rounded, not truncated)
+          lo[4 * i + 0] = __float_as_uint(tf32_rn_fast(x.x - h0)); lo[4 * i + 1] = __float_as_uint(tf32_rn_fast(x.y - h1));
+          lo[4 * i + 2] = __float_as_uint(tf32_rn_fast(x.z - h2)); lo[4 * i + 3] = __float_as_uint(tf32_rn_fast(x.w - h3));
+        } else {
+          lo[2 * i + 0] = pack_bf16x2(x.x - h0, x.y - h1);
+          lo[2 * i + 1] = pack_bf16x2(x.z - h2, x.w - h3);
+          lo[16 + 2 * i + 0] = pack_bf16x2(h0, h1);
+          lo[16 + 2 * i + 1] = pack_bf16x2(h2, h3);
+        }
       }
     };
     TcGroupOf gof;                            // which issuer waits for the chunk being converted
@@ -603,10 +615,15 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         const float h0 = tf32_rn_fast(x.x), h1 = tf32_rn_fast(x.y), h2 = tf32_rn_fast(x.z), h3 = tf32_rn_fast(x.w);
         hi[4 * i + 0] = __float_as_uint(h0); hi[4 * i + 1] = __float_as_uint(h1);
         hi[4 * i + 2] = __float_as_uint(h2); hi[4 * i + 3] = __float_as_uint(h3);
-        lo[2 * i + 0] = pack_bf16x2(x.x - h0, x.y - h1);
-        lo[2 * i + 1] = pack_bf16x2(x.z - h2, x.w - h3);
-        lo[16 + 2 * i + 0] = pack_bf16x2(h0, h1);
-        lo[16 + 2 * i + 1] = pack_bf16x2(h2, h3);
+        if (PREC == 1) {
+          lo[4 * i + 0] = __float_as_uint(tf32_rn_fast(x.x - h0)); lo[4 * i + 1] = __float_as_uint(tf32_rn_fast(x.y - h1));
+          lo[4 * i + 2] = __float_as_uint(tf32_rn_fast(x.z - h2)); lo[4 * i + 3] = __float_as_uint(tf32_rn_fast(x.w - h3));
+        } else {
+          lo[2 * i + 0] = pack_bf16x2(x.x - h0, x.y - h1);
+          lo[2 * i + 1] = pack_bf16x2(x.z - h2, x.w - h3);
+          lo[16 + 2 * i + 0] = pack_bf16x2(h0, h1);
+          lo[16 + 2 * i + 1] = pack_bf16x2(h2, h3);
+        }
       }
       __syncwarp();                         // slot free
       if (DBG == 6) { long long tq1 = clock64(); tA_x += tq1 - tq0; tq0 = tq1; }
@@ -674,11 +691,11 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
             const uint32_t dst = sbase + stage * TC_STAGE_BYTES + crank * (R * 128);
             const uint16_t mask = (uint16_t)((1u << TC_CLUSTER) - 1);
             tma_load_2d_mc(dst, &map_hi, full, c * TC_BK, n0 + R * (int)crank, mask);
-            tma_load_2d_mc(dst + 16384, &map_lo, full, c * 2 * TC_BK, n0 + R * (int)crank, mask);   // bf16 [hi | lo] row of this chunk
+            tma_load_2d_mc(dst + 16384, &map_lo, full, (PREC == 1 ? 1 : 2) * c * TC_BK, n0 + R * (int)crank, mask);   // bf16 [hi | lo] row of this chunk (PREC 1: fp32 lo tile)
           } else {
             const uint32_t dst = sbase + stage * TC_STAGE_BYTES;
             tma_load_2d(dst, &map_hi, full, c * TC_BK, n0);
-            tma_load_2d(dst + 16384, &map_lo, full, c * 2 * TC_BK, n0);
+            tma_load_2d(dst + 16384, &map_lo, full, (PREC == 1 ? 1 : 2) * c * TC_BK, n0);
           }
           if (++stage == TC_BSTAGES) { stage = 0; phase ^= 1; }
         }
@@ -763,6 +780,10 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
               for (int k = 0; k < TC_BK / 8; ++k) {
                 const uint64_t adv = (uint64_t)(k * 2);      // 8 fp32 = 32 B = 2 x 16 B
                 if (DBG != 7) umma_tf32_ts(d_main, a_hi + 8 * k, b_hi + adv, TC_IDESC, (cg | k) ? 1u : 0u);
+                if (PREC == 1) {
+                  umma_tf32_ts(d_main, a_pk + 8 * k, b_hi + adv, TC_IDESC, 1u);
+                  umma_tf32_ts(d_main, a_hi + 8 * k, b_pk + adv, TC_IDESC, 1u);
+                } else
                 if (DBG != 3) umma_bf16_ts(d_main, a_pk + 8 * k, b_pk + adv, TC_IDESC_BF, (DBG == 7 && !(cg | k)) ? 0u : 1u);
               }
               if (TC_CLUSTER > 1) umma_commit_mc(bar0 + BB_EMPTY + 8 * bs, (uint16_t)((1u << TC_CLUSTER) - 1));
@@ -834,6 +855,10 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
             for (int k = 0; k < TC_BK / 8; ++k) {
               const uint64_t adv = (uint64_t)(k * 2);      // 8 fp32 = 32 B = 2 x 16 B
               if (DBG != 7) umma_tf32_ts(d_main, a_hi + 8 * k, b_hi + adv, TC_IDESC, (cg | k) ? 1u : 0u);
+              if (PREC == 1) {                  // 3xTF32: A_lo.B_hi and A_hi.B_lo as tf32 products of their own
+                umma_tf32_ts(d_main, a_pk + 8 * k, b_hi + adv, TC_IDESC, 1u);
+                umma_tf32_ts(d_main, a_hi + 8 * k, b_pk + adv, TC_IDESC, 1u);
+              } else
               // correction: bf16 k-step k of the K=64 row [A_lo | A_hi] . [B_hi | B_lo]^T (8 columns of bf16
               // pairs in tensor memory, 32 bytes of the swizzled B row, like a tf32 k-step).  (Issuing the four
               // tf32 MMAs first and the four bf16 ones after them measured 5 % slower than interleaving them.)
@@ -1264,7 +1289,7 @@ constexpr float TC_TRUNC_C = 3.5e-8f;
 // `pk` is the bf16 operand of the correction product: row n, chunk c (32 k's) holds
 // [hi(k = 32c .. 32c+31) | lo(k = 32c .. 32c+31)] as 64 bf16 = one 128-byte swizzle row of the B stage.
 __global__ void tc_split_kernel(const float* __restrict__ w, float* __restrict__ hi, unsigned short* __restrict__ pk,
-                                long long n, int K, int semch) {
+                                long long n, int K, int semch, int prec) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   long long src = i;
@@ -1282,10 +1307,16 @@ __global__ void tc_split_kernel(const float* __restrict__ w, float* __restrict__
   const int glen = min(TC_FLUSH, nchunks - g * TC_FLUSH);            // chunks in this flush group
   // MMA index of this product inside its flush group: a chunk issues 8 MMAs into the group's accumulator, in the
   // order main(k-step 0), correction(0), main(1), correction(1), ...; every one of them truncates the accumulator
-  const int s = (c - g * TC_FLUSH) * (2 * TC_BK / 8) + 2 * ((k % TC_BK) / 8);
-  const float steps_left = (float)(glen * (2 * TC_BK / 8) - s);      // truncations this product still sees
+  // (prec 1, 3xTF32: 12 MMAs per chunk in the order main(k), A_lo.B_hi(k), A_hi.B_lo(k))
+  const int per_k = prec == 1 ? 3 : 2;
+  const int s = (c - g * TC_FLUSH) * (per_k * TC_BK / 8) + per_k * ((k % TC_BK) / 8);
+  const float steps_left = (float)(glen * (per_k * TC_BK / 8) - s);      // truncations this product still sees
   hi[i] = h;
   const float lo = (x - h) + TC_TRUNC_C * steps_left * h;
+  if (prec == 1) {                       // fp32 lo matrix [N][K], the tf32 operand of the A_hi.B_lo product
+    reinterpret_cast<float*>(pk)[i] = tf32_rna(lo);
+    return;
+  }
   unsigned short* prow = pk + row * 2 * K + (long long)c * 2 * TC_BK + (k - c * TC_BK);
   prow[0] = __bfloat16_as_ushort(__float2bfloat16_rn(h));
   prow[TC_BK] = __bfloat16_as_ushort(__float2bfloat16_rn(lo));
@@ -1310,19 +1341,19 @@ inline tc_encode_fn tc_get_encode() {
 // W: [N][K] fp32 K-major (device).  Allocates hi/lo once, splits, encodes the TMA maps.
 // Returns 0 on success, a cudaError_t / -1 otherwise.
 inline int tc_prepare_weights(TcWeights& t, const float* W, int N, int K, cudaStream_t st,
-                              std::vector<void*>* owned, int semch = 0) {
+                              std::vector<void*>* owned, int semch = 0, int prec = 0) {
   t.ready = false;
   if (K % TC_BK != 0 || N % 4 != 0) return 0;            // shape not taken by this core (FFMA runs it)
   tc_encode_fn enc = tc_get_encode();
   if (!enc) return -1;
-  if (!t.hi || t.N != N || t.K != K) {
+  if (!t.hi || t.N != N || t.K != K || t.prec != prec) {
     void* a = nullptr; void* b = nullptr;
     cudaError_t e = cudaMalloc(&a, sizeof(float) * (size_t)N * K);
     if (e != cudaSuccess) return (int)e;
     e = cudaMalloc(&b, sizeof(float) * (size_t)N * K);
     if (e != cudaSuccess) return (int)e;
     owned->push_back(a); owned->push_back(b);
-    t.hi = (float*)a; t.lo = (float*)b; t.N = N; t.K = K;
+    t.hi = (float*)a; t.lo = (float*)b; t.N = N; t.K = K; t.prec = prec;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
     cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)(TC_BN / TC_CLUSTER)};   // each CTA fetches its share
@@ -1333,14 +1364,18 @@ inline int tc_prepare_weights(TcWeights& t, const float* W, int N, int K, cudaSt
     // the bf16 [hi | lo] rows: [N][2K] bf16 (the same bytes per row as the fp32 matrix), 64 elements = 128 B per box row
     cuuint64_t dims_b[2] = {(cuuint64_t)2 * K, (cuuint64_t)N};
     cuuint32_t box_b[2] = {(cuuint32_t)(2 * TC_BK), (cuuint32_t)(TC_BN / TC_CLUSTER)};
-    CUresult r2 = enc(&t.map_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, t.lo, dims_b, strides, box_b, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = prec == 1
+        ? enc(&t.map_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, t.lo, dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+        : enc(&t.map_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, t.lo, dims_b, strides, box_b, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return -1;
   }
   long long n = (long long)N * K;
   if (semch && N % 128) return -1;
-  tc_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, t.hi, reinterpret_cast<unsigned short*>(t.lo), n, K, semch);
+  tc_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, t.hi, reinterpret_cast<unsigned short*>(t.lo), n, K, semch, prec);
   t.ready = true;
   return 0;
 }
@@ -1410,7 +1445,7 @@ inline void tc_build_amaps(GemmP& p, TcAMaps& am) {
   p.a_tma = am.ok ? 1 : 0;
 }
 
-template <int EPI, int DBG>
+template <int EPI, int DBG, int PREC = 0>
 inline int tc_launch_one(int grid, cudaStream_t st, const GemmP& p_in, const TcWeights& t, int nt, int items) {
   GemmP p = p_in;
   TcAMaps am;
@@ -1420,7 +1455,7 @@ inline int tc_launch_one(int grid, cudaStream_t st, const GemmP& p_in, const TcW
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)gemm_tc_kernel<EPI, DBG>,
+    cudaError_t e = cudaFuncSetAttribute((const void*)gemm_tc_kernel<EPI, DBG, PREC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set[dev & 63] = true;
@@ -1438,7 +1473,7 @@ inline int tc_launch_one(int grid, cudaStream_t st, const GemmP& p_in, const TcW
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return (int)cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, DBG>, p, t.map_hi, t.map_lo, am.m[0], am.m[1], am.m[2], nt, items);
+  return (int)cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, DBG, PREC>, p, t.map_hi, t.map_lo, am.m[0], am.m[1], am.m[2], nt, items);
 }
 
 inline int tc_launch(int sm_count, cudaStream_t st, int epi, const GemmP& p, const TcWeights& t, int dbg = 0) {
@@ -1448,6 +1483,10 @@ inline int tc_launch(int sm_count, cudaStream_t st, int epi, const GemmP& p, con
   if (items > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
   const int max_cl = sm_count / TC_CLUSTER;
   const int grid = TC_CLUSTER * (int)(items < max_cl ? items : max_cl);
+  if (t.prec == 1) {                       // 3xTF32 (training): plain epilogue only
+    if (epi != EPI_PLAIN || dbg) return (int)cudaErrorInvalidValue;
+    return tc_launch_one<EPI_PLAIN, 0, 1>(grid, st, p, t, nt, (int)items);
+  }
   if (dbg) {
     if (epi != EPI_PLAIN) return (int)cudaErrorInvalidValue;
     switch (dbg) {

@@ -14,6 +14,7 @@
 struct TCtx {
   gast_handle* h; cudaStream_t st; Arena* a; Lookup* L; int J;
   bool dry;   // sizing pass: no launches
+  int tc_slot = 0;   // next slot of the handle's table of per-GEMM tcgen05 operand copies (train_tcw)
   float* fl(size_t n) { return a->take(n); }
   double* dbl(size_t n) { return reinterpret_cast<double*>(a->take(2 * n)); }
   unsigned char* bytes(size_t n) { return reinterpret_cast<unsigned char*>(a->take((n + 3) / 4)); }
@@ -24,6 +25,20 @@ static float* grad_ptr(gast_handle* h, const std::string& key, int64_t numel) {
   if (it == h->grads.end()) { fail("gradient buffer for '%s' is not bound", key.c_str()); return nullptr; }
   if (it->second.numel != numel) { fail("gradient buffer '%s' has the wrong size", key.c_str()); return nullptr; }
   return reinterpret_cast<float*>(it->second.ptr);
+}
+
+// tcgen05 operand copies of one training GEMM's weight matrix (forward: the raw weights, backward: their transposes):
+// the weights change every step, so the hi/lo split runs per call; buffers and tensor maps live in a per-handle table
+// indexed by the GEMM's position in the step (the sequence of GEMMs of a model is fixed).  3xTF32 arithmetic (PREC 1 of
+// gemm_tc.cuh): per-GEMM error 3e-7 rms, the same as the exact-fp32 FFMA kernel it replaces, so the gradient-noise bars
+// of tests/test_gpu_train.py hold unchanged.  Shapes the core does not take (K % 32: the expand conv) stay on FFMA.
+static const TcWeights* train_tcw(TCtx& c, const float* W, int N, int K) {
+  const size_t slot = (size_t)c.tc_slot++;
+  if (c.h->gemm_core != 0 || !c.h->train_tc_on) return nullptr;
+  if (c.h->train_tc.size() <= slot) c.h->train_tc.resize(slot + 1);
+  TcWeights& t = c.h->train_tc[slot];
+  if (tc_prepare_weights(t, W, N, K, c.st, &c.h->owned, 0, 1)) return nullptr;
+  return t.ready ? &t : nullptr;
 }
 
 // dense out[M][N] = A[M][K] . W[N][K]^T (+bias), rows are plain (no frame structure)
@@ -38,7 +53,7 @@ static int dense_nt(TCtx& c, const float* A, int lda, const float* W, long long 
   p.seg[0].base = A; p.seg[0].ld = lda; p.seg[0].K = K; p.seg[0].Kc = K; p.seg[0].tap_stride = 0;
   p.seg[0].map = RowMap{1, 1, 1, 0};
   p.W = W; p.ldw = K; p.N = N; p.out = out; p.ld_out = ldo; p.bias = bias;
-  return launch_gemm(c.h, c.st, EPI_PLAIN, p, nullptr);
+  return launch_gemm(c.h, c.st, EPI_PLAIN, p, train_tcw(c, W, N, K));
 }
 
 // frame-structured forward GEMM with gathered segments (same kernel as inference), raw weights
@@ -50,7 +65,7 @@ static int seg_gemm(TCtx& c, const ASeg* segs, int nseg, const float* W, int ldw
   p.nseg = nseg;
   for (int i = 0; i < nseg; ++i) p.seg[i] = segs[i];
   p.W = W; p.ldw = ldw; p.N = N; p.out = out; p.ld_out = ldo; p.bias = bias;
-  return launch_gemm(c.h, c.st, EPI_PLAIN, p, nullptr);
+  return launch_gemm(c.h, c.st, EPI_PLAIN, p, train_tcw(c, W, N, ldw));
 }
 
 static long long pad32(long long m) { return (m + 31) / 32 * 32; }
@@ -450,7 +465,7 @@ static int train_backward(gast_handle* h, TCtx& c, TrainState& ts, const float* 
     float* gws = grad_ptr(h, "shrink.weight", (int64_t)3 * Cl);
     if (!c.L->ok || !gws) return 1;
     shrink_bwd_x_kernel<<<cdiv(F * J * Cl, 256), 256, 0, c.st>>>(dy, ws, F * J, Cl, dcur);
-    shrink_bwd_w_kernel<<<cdiv((long long)3 * Cl, 128), 128, 0, c.st>>>(dy, ts.last, F * J, Cl, gws);
+    shrink_bwd_w_kernel<<<cdiv(Cl, 32), dim3(32, SBW_RG), 0, c.st>>>(dy, ts.last, F * J, Cl, gws);
   }
   for (int i = L - 1; i >= 1; --i) {
     StageSave& s = ts.stages[i - 1];

@@ -612,14 +612,33 @@ __global__ void shrink_bwd_x_kernel(const float* __restrict__ dy, const float* _
   int k = (int)(idx - m * K);
   dX[idx] = dy[m * 3] * Ws[k] + dy[m * 3 + 1] * Ws[K + k] + dy[m * 3 + 2] * Ws[2 * K + k];
 }
-__global__ void shrink_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ X, long long M, int K,
-                                    float* __restrict__ dWs) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 3 * K) return;
-  int o = idx / K, k = idx - o * K;
-  double s = 0.0;
-  for (long long m = 0; m < M; ++m) s += (double)dy[m * 3 + o] * (double)X[m * K + k];
-  dWs[idx] = (float)s;
+// block = 32 columns k x SBW_RG row groups; fixed-order reduction over the row groups (deterministic).  (One thread per
+// output walking all M rows serially took 0.32 ms per step at b = 128: 3.5 % of the step for a 3 x 1024 matrix.)
+constexpr int SBW_RG = 16;
+__global__ void __launch_bounds__(32 * SBW_RG)
+shrink_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ X, long long M, int K,
+                    float* __restrict__ dWs) {
+  __shared__ double part[SBW_RG][3][33];
+  const int kx = threadIdx.x, rg = threadIdx.y;
+  const int k = blockIdx.x * 32 + kx;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  if (k < K) {
+#pragma unroll 4
+    for (long long m = rg; m < M; m += SBW_RG) {
+      const double x = (double)X[m * K + k];
+      s0 += (double)__ldg(dy + m * 3 + 0) * x;
+      s1 += (double)__ldg(dy + m * 3 + 1) * x;
+      s2 += (double)__ldg(dy + m * 3 + 2) * x;
+    }
+  }
+  part[rg][0][kx] = s0; part[rg][1][kx] = s1; part[rg][2][kx] = s2;
+  __syncthreads();
+  if (rg < 3 && k < K) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < SBW_RG; ++i) t += part[i][rg][kx];
+    dWs[(long long)rg * K + k] = (float)t;
+  }
 }
 
 // conv weight gradient re-layout: GEMM order [n][tap*Cin + c]  ->  parameter order (n, c, tap)

@@ -23,6 +23,9 @@ class DataParallelTrainer(object):
         self.model = model
         self.group = group
         self.flat = FlatGradBuffer(model.parameters())        # .grad of every parameter aliases one buffer
+        # one backward per step into buffers this trainer owns and zeroes: the library writes the gradients in place
+        # (engine._TrainFn.backward) instead of handing 166 tensors to autograd's per-parameter accumulation
+        model.__dict__['_gast_direct_grads'] = True
         self.opt = optimizer_factory(model.parameters())
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
 

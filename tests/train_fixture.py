@@ -77,6 +77,11 @@ def check_step(g, step, y, loss, grads, y_tol, loss_rtol, ent_rtol, norm_rtol, r
     # rounding noise in ANY implementation, the reference included: they only have to stay noise-sized
     gmax = max(float(g['gsum%d/%s' % (step, k)][0]) for k in g['meta']['names'])
     worst = (0.0, None)
+    # Step 0, gradients within 1e-3 of the noise floor (norm < 1e-3 of the largest gradient: the theta/phi biases of the
+    # attention heads, whose gradient is a sum over all rows that cancels to ~2e-5 of the others): the reference's
+    # own two runs differ by `alt_dg0` there (4.4 % at configs[2], stored in the fixture), so these few tensors are held
+    # to band_factor x that band; every other gradient keeps the fixed tolerances.
+    band0 = self_noise(g, 0) if step == 0 else None
     for k in g['meta']['names']:
         ns_ref, ent_ref = g['gsum%d/%s' % (step, k)], g['gent%d/%s' % (step, k)]
         ns, ent = digest(grads[k], g['idx/' + k])
@@ -88,9 +93,12 @@ def check_step(g, step, y, loss, grads, y_tol, loss_rtol, ent_rtol, norm_rtol, r
         ee = float(np.abs(ent - ent_ref).max() / np.abs(ent_ref).max())
         if max(en, ee) > worst[0]:
             worst = (max(en, ee), k)
-        if not en < norm_rtol:
+        tn, te = norm_rtol, ent_rtol
+        if band0 is not None and ns_ref[0] < 1e-3 * gmax:
+            tn, te = max(tn, band_factor * band0[3]), max(te, band_factor * band0[3])
+        if not en < tn:
             bad.append(('grad norm', step, k, ns[0], ns_ref[0]))
-        if not ee < ent_rtol:
+        if not ee < te:
             bad.append(('grad entries', step, k, ee))
     if report is not None:
         report.append(('step %d: max|dy| %.3g  loss rel %.3g  worst grad fingerprint %.3g (%s)  violations %d%s'

@@ -105,6 +105,7 @@ def main():
             ref = A.astype(np.float64) @ W.astype(np.float64).T
             stats('K=%4d %-8s FFMA fp32' % (K, kind), gemm(A, W, 1, 0), ref)
             stats('K=%4d %-8s tcgen05 tf32+bf16corr' % (K, kind), gemm(A, W, 0, 0), ref)
+            stats('K=%4d %-8s tcgen05 3xTF32 (training)' % (K, kind), gemm(A, W, 2, 0), ref)
             Ah, Wh = tf32_round(A), tf32_round(W)
             refh = Ah.astype(np.float64) @ Wh.astype(np.float64).T
             stats('K=%4d %-8s tcgen05 hi.hi vs exact(hi.hi)' % (K, kind), gemm(Ah, Wh, 0, 0), refh)
