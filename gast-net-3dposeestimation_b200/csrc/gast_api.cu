@@ -99,6 +99,7 @@ struct gast_handle {
   // training: per-GEMM tcgen05 operand copies (3xTF32), indexed by the GEMM's position in the step (train.cuh)
   std::vector<TcWeights> train_tc;
   bool train_tc_on = true;
+  int block1_slabs = 1;              // clip slabs of the expand stage + first block (GAST_BLOCK1_SLABS)
   // optional per-launch device timing (bench.py roofline): event pairs around every launch
   bool timing = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -207,6 +208,7 @@ extern "C" int gast_create(gast_t** out, const gast_cfg* cfg) {
   h->cfg = *cfg;
   h->sm_count = prop.multiProcessorCount;
   h->fpt = 128 / J;
+  if (const char* e = getenv("GAST_BLOCK1_SLABS")) h->block1_slabs = std::max(1, atoi(e));
   if (const char* e = getenv("GAST_TRAIN_TC")) h->train_tc_on = atoi(e) != 0;   // 0: training GEMMs on the FFMA core (A/B runs)
   h->sym_r.assign(cfg->sym_rows, cfg->sym_rows + cfg->sym_nnz);
   h->sym_c.assign(cfg->sym_cols, cfg->sym_cols + cfg->sym_nnz);
@@ -669,13 +671,19 @@ static int run_global(gast_handle* h, cudaStream_t st, BlockConsts& b, const flo
     p.nseg = 1; p.seg[0] = seg_flat(X, C, C);
     p.W = b.Wg; p.ldw = C; p.N = Ng; p.out = out_G; p.ld_out = Ng; p.bias = b.bg; p.relu = 0;
     if (launch_gemm(h, st, EPI_PLAIN, p, &b.tc_g)) return 1;
-    const int G4 = Ng / 4;
-    int fpb = G4 >= MIX_THREADS ? 1 : MIX_THREADS / G4;
+    static const int mix_v = getenv("GAST_MIX_V") ? atoi(getenv("GAST_MIX_V")) : 4;   // channels per thread (4 or 2)
+    const int vn = (mix_v == 2 && b.Cg % 2 == 0) ? 2 : 4;
+    const int GV = Ng / vn;
+    const int nthr = (vn == 2) ? 2 * MIX_THREADS : MIX_THREADS;
+    int fpb = GV >= nthr ? 1 : nthr / GV;
     fpb = std::max(1, std::min(fpb, (int)(40 * 1024 / (sizeof(float) * b.heads * J * MIX_JP))));   // attention rows fit 40 KB
     const size_t smem = sizeof(float) * (size_t)fpb * b.heads * J * MIX_JP;
     {
       TimedLaunch tl(h, st, LK_GLOBAL_MIX);
-      global_mix_kernel<<<cdiv(F, fpb), MIX_THREADS, smem, st>>>(out_G, Ng, w.AB, b.Ck, w.Y, Ng, F, J, b.heads, b.Cg, fpb);
+      if (vn == 2)
+        global_mix_kernel<float2, 2 * MIX_THREADS><<<cdiv(F, fpb), 2 * MIX_THREADS, smem, st>>>(out_G, Ng, w.AB, b.Ck, w.Y, Ng, F, J, b.heads, b.Cg, fpb);
+      else
+        global_mix_kernel<float4, MIX_THREADS><<<cdiv(F, fpb), MIX_THREADS, smem, st>>>(out_G, Ng, w.AB, b.Ck, w.Y, Ng, F, J, b.heads, b.Cg, fpb);
       h->launches++;
     }
     CUDA_OK(cudaGetLastError());
@@ -702,8 +710,14 @@ static int run_global(gast_handle* h, cudaStream_t st, BlockConsts& b, const flo
 static int run_block(gast_handle* h, cudaStream_t st, BlockConsts& b, const float* X, long long F,
                      const BlockBufs& w, float* out) {
   const int C = b.C;
-  if (run_local(h, st, b, X, F, w, w.L, GAST_KIND_BLOCK)) return 1;
-  if (run_global(h, st, b, X, F, w, w.Gl, GAST_KIND_BLOCK)) return 1;
+  static const bool global_first = getenv("GAST_BLOCK_ORDER") && atoi(getenv("GAST_BLOCK_ORDER")) != 0;   // experiment
+  if (global_first) {
+    if (run_global(h, st, b, X, F, w, w.Gl, GAST_KIND_BLOCK)) return 1;
+    if (run_local(h, st, b, X, F, w, w.L, GAST_KIND_BLOCK)) return 1;
+  } else {
+    if (run_local(h, st, b, X, F, w, w.L, GAST_KIND_BLOCK)) return 1;
+    if (run_global(h, st, b, X, F, w, w.Gl, GAST_KIND_BLOCK)) return 1;
+  }
   GemmP p;
   gemm_defaults_flat(p, h, F);
   p.nseg = 3;
@@ -793,25 +807,34 @@ extern "C" int gast_forward(gast_t* h, const float* x, float* y, int32_t B, int3
   if (plan_model(h, B, T, strided_now, a, &mb, &g)) return 1;
   const gast_cfg& c = h->cfg;
   const int C = c.channels, L = c.num_stages;
-  // expand (gast_net.py:163-164)
+  // expand (gast_net.py:163-164) + first GraphAttentionBlock, optionally in SLABS of clips: the layers of block 1 are
+  // the HBM-bound ones (K = C GEMMs, row dots, attention mix, expand), and a slab whose intermediates fit the 126 MB L2
+  // hands them from producer to consumer on chip; the block temporaries are reused by every slab.
   long long F = (long long)B * g.T0;
-  {
-    long long rows = F * J;
-    if (rows >= 0x7fffffffLL) return fail("expand: more than 2^31 positions in one call");
-    if (c.filter_widths[0] * c.in_features > EXP_MAXKF) return fail("expand: filter_width*in_features > %d unsupported", EXP_MAXKF);
-    long long thr = ((rows + EXP_ROWS - 1) / EXP_ROWS) * (C / 4);
-    TimedLaunch tl(h, st, LK_EXPAND);
-    if (c.filter_widths[0] * c.in_features <= 6)
-      expand_kernel<6><<<cdiv(thr, 256), 256, 0, st>>>(x, h->We, h->be, mb.act[0], rows, J, T, g.T0, g.s0,
-                                                      c.filter_widths[0], c.in_features, C);
-    else
-      expand_kernel<EXP_MAXKF><<<cdiv(thr, 256), 256, 0, st>>>(x, h->We, h->be, mb.act[0], rows, J, T, g.T0, g.s0,
-                                                              c.filter_widths[0], c.in_features, C);
-    h->launches++;
+  if (F * J >= 0x7fffffffLL) return fail("expand: more than 2^31 positions in one call");
+  if (c.filter_widths[0] * c.in_features > EXP_MAXKF) return fail("expand: filter_width*in_features > %d unsupported", EXP_MAXKF);
+  const int nslab = std::max(1, std::min(h->block1_slabs, B));
+  const int Bs = (B + nslab - 1) / nslab;
+  for (int b0 = 0; b0 < B; b0 += Bs) {
+    const int nb = std::min(Bs, B - b0);
+    const long long Fs = (long long)nb * g.T0, rows = Fs * J;
+    const float* xs = x + (long long)b0 * T * J * c.in_features;
+    float* a0 = mb.act[0] + (long long)b0 * g.T0 * J * C;
+    float* a1 = mb.act[1] + (long long)b0 * g.T0 * J * 2 * C;
+    {
+      long long thr = ((rows + EXP_ROWS - 1) / EXP_ROWS) * (C / 4);
+      TimedLaunch tl(h, st, LK_EXPAND);
+      if (c.filter_widths[0] * c.in_features <= 6)
+        expand_kernel<6><<<cdiv(thr, 256), 256, 0, st>>>(xs, h->We, h->be, a0, rows, J, T, g.T0, g.s0,
+                                                        c.filter_widths[0], c.in_features, C);
+      else
+        expand_kernel<EXP_MAXKF><<<cdiv(thr, 256), 256, 0, st>>>(xs, h->We, h->be, a0, rows, J, T, g.T0, g.s0,
+                                                                c.filter_widths[0], c.in_features, C);
+      h->launches++;
+    }
+    if (run_block(h, st, h->blocks[0], a0, Fs, mb.bb, a1)) return 1;
   }
-  int cur = 0;
-  if (run_block(h, st, h->blocks[0], mb.act[0], F, mb.bb, mb.act[1])) return 1;
-  cur = 1;
+  int cur = 1;
   int Tp = g.T0;
   for (int i = 1; i < L; ++i) {
     StageConsts& s = h->stages[i - 1];

@@ -89,6 +89,9 @@ static_assert(TC_REG_A + 2 * TC_REG_E + TC_REG_M <= 512, "register file over-sub
 #define GAST_TC_CONV_PIPE 1
 #endif
 constexpr int TC_CONV_PIPE = GAST_TC_CONV_PIPE;
+#ifndef GAST_TC_TRUNC_SPLIT
+#define GAST_TC_TRUNC_SPLIT 0
+#endif
 
 // MMA issue: 1 = two issuing warps (9 and 11) take alternate flush groups (each owns one accumulator buffer and its
 // own set of operand "full" barriers), 0 = warp 9 issues everything
@@ -534,6 +537,24 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 x = xr[i];
+#if GAST_TC_TRUNC_SPLIT
+        if (PREC == 0) {
+          // split by TRUNCATION: the raw value is the tf32 operand (the tensor core reads the upper 19 bits), the
+          // correction is x - trunc(x): one integer op per element less than rounding.  Alone it measured no faster
+          // (the single MMA issuer paces the chunk rate then, experiment 11); with two issuers the converters are
+          // the limiter (experiment 10), so the two are meant to be used together.  Costs a bit of accuracy: the
+          // remainder is one-signed and up to 2^-10 |x| (per-GEMM error 3.2e-6 instead of 2.1e-6 rms).
+          const float t0 = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u), t1 = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          const float t2 = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u), t3 = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          hi[4 * i + 0] = __float_as_uint(x.x); hi[4 * i + 1] = __float_as_uint(x.y);
+          hi[4 * i + 2] = __float_as_uint(x.z); hi[4 * i + 3] = __float_as_uint(x.w);
+          lo[2 * i + 0] = pack_bf16x2(x.x - t0, x.y - t1);
+          lo[2 * i + 1] = pack_bf16x2(x.z - t2, x.w - t3);
+          lo[16 + 2 * i + 0] = pack_bf16x2(x.x, x.y);
+          lo[16 + 2 * i + 1] = pack_bf16x2(x.z, x.w);
+          continue;
+        }
+#endif
         // (splitting by TRUNCATION -- the raw value as the tf32 operand, x - trunc(x) as the correction -- saves an
         //  integer op per element but measured no faster and doubles the error of the bf16 correction:
         //  profiles/r02_tc_attribution.md, experiment 11)
@@ -1460,8 +1481,7 @@ inline int tc_launch_one(int grid, cudaStream_t st, const GemmP& p_in, const TcW
     if (e != cudaSuccess) return (int)e;
     attr_set[dev & 63] = true;
   }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = TC_SMEM_BYTES;

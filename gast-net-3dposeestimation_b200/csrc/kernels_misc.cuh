@@ -247,7 +247,27 @@ constexpr int MIX_THREADS = 128;
 constexpr int MIX_JMAX = 20;
 constexpr int MIX_JP = 20;        // padded row length of an attention row in shared memory (float4 reads)
 
-__global__ void __launch_bounds__(MIX_THREADS)
+template <typename V> struct MixVec;
+template <> struct MixVec<float4> {
+  static constexpr int N = 4;
+  __device__ static float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ static float4 load(const float* p) { return ldg4(p); }
+  __device__ static void fma(float a, const float4& g, float4& o) {
+    o.x = fmaf(a, g.x, o.x); o.y = fmaf(a, g.y, o.y); o.z = fmaf(a, g.z, o.z); o.w = fmaf(a, g.w, o.w);
+  }
+};
+template <> struct MixVec<float2> {
+  static constexpr int N = 2;
+  __device__ static float2 zero() { return make_float2(0.f, 0.f); }
+  __device__ static float2 load(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+  __device__ static void fma(float a, const float2& g, float2& o) { o.x = fmaf(a, g.x, o.x); o.y = fmaf(a, g.y, o.y); }
+};
+
+// V = float4: one thread = (frame, 4 channels), 17 float4 of g in registers (120 registers, 16 warps per SM);
+// V = float2: (frame, 2 channels), half the registers per thread and twice the warps in flight per SM -- the kernel
+// is latency-bound (25-30 % of the issue slots, 43 % of the HBM rate with float4), so occupancy is what it lacks.
+template <typename V, int NT>
+__global__ void __launch_bounds__(NT, (MixVec<V>::N == 2) ? 4 : 1)
 global_mix_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ ab, const float* __restrict__ ck,
                   float* __restrict__ Y, int ldy, long long F, int J, int heads, int Cg, int fpb) {
   extern __shared__ __align__(16) float att_s[];            // [fpb][heads][J][MIX_JP]
@@ -256,7 +276,7 @@ global_mix_kernel(const float* __restrict__ G, int ldg, const float* __restrict_
   const long long f0 = (long long)blockIdx.x * fpb;
   // ---- attention rows of this block's frames
   const int nrow = fpb * heads * J;
-  for (int e = tid; e < nrow; e += MIX_THREADS) {
+  for (int e = tid; e < nrow; e += NT) {
     const int i = e % J, h = (e / J) % heads, fs = e / (J * heads);
     const long long f = f0 + fs;
     float* dst = att_s + (size_t)e * MIX_JP;
@@ -287,18 +307,19 @@ global_mix_kernel(const float* __restrict__ G, int ldg, const float* __restrict_
     }
   }
   __syncthreads();
-  // ---- mix: thread = (frame slot, group of 4 channels)
-  const int G4 = (heads * Cg) >> 2;
-  for (int w = tid; w < fpb * G4; w += MIX_THREADS) {
-    const int fs = w / G4, c = (w - fs * G4) * 4;
+  // ---- mix: thread = (frame slot, group of V::N channels)
+  constexpr int VN = MixVec<V>::N;
+  const int GV = (heads * Cg) / VN;
+  for (int w = tid; w < fpb * GV; w += NT) {
+    const int fs = w / GV, c = (w - fs * GV) * VN;
     const long long f = f0 + fs;
     if (f >= F) continue;
     const int h = c / Cg;
-    float4 g[MIX_JMAX];
+    V g[MIX_JMAX];
     const float* gp = G + (f * J) * (long long)ldg + c;
 #pragma unroll
     for (int j = 0; j < MIX_JMAX; ++j)
-      if (j < J) g[j] = ldg4(gp + (long long)j * ldg);
+      if (j < J) g[j] = MixVec<V>::load(gp + (long long)j * ldg);
     const float* arow = att_s + (size_t)((fs * heads + h) * J) * MIX_JP;
     float* yp = Y + (f * J) * (long long)ldy + c;
     for (int i = 0; i < J; ++i) {
@@ -308,14 +329,11 @@ global_mix_kernel(const float* __restrict__ G, int ldg, const float* __restrict_
         const float4 t = *reinterpret_cast<const float4*>(arow + i * MIX_JP + q * 4);
         a[q * 4] = t.x; a[q * 4 + 1] = t.y; a[q * 4 + 2] = t.z; a[q * 4 + 3] = t.w;
       }
-      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      V o = MixVec<V>::zero();
 #pragma unroll
       for (int j = 0; j < MIX_JMAX; ++j)
-        if (j < J) {
-          o.x = fmaf(a[j], g[j].x, o.x); o.y = fmaf(a[j], g[j].y, o.y);
-          o.z = fmaf(a[j], g[j].z, o.z); o.w = fmaf(a[j], g[j].w, o.w);
-        }
-      *reinterpret_cast<float4*>(yp + (long long)i * ldy) = o;
+        if (j < J) MixVec<V>::fma(a[j], g[j], o);
+      *reinterpret_cast<V*>(yp + (long long)i * ldy) = o;
     }
   }
 }

@@ -267,6 +267,7 @@ static int block_bwd(TCtx& c, BlockSave& b, BlockConsts& bc, const float* dOut, 
   float* dG = c.fl((size_t)M * C);
   float* dab = c.fl((size_t)M * 8);
   float* dCk = c.fl((size_t)4 * J * J);
+  float* dCkp = c.fl((size_t)F * 4 * J * J);     // per-frame contributions, reduced in a fixed order
   float* dWg = c.fl((size_t)C * C);
   float* dU = c.fl((size_t)8 * C);
   double* dsum = c.dbl((size_t)C + 8);
@@ -274,9 +275,9 @@ static int block_bwd(TCtx& c, BlockSave& b, BlockConsts& bc, const float* dOut, 
   float* dcab = c.fl(8);
   float* dXg = c.fl((size_t)M * C);
   if (!c.dry) {
-    cudaMemsetAsync(dCk, 0, sizeof(float) * 4 * J * J, c.st);
     att_mix_bwd_kernel<<<(unsigned)F, 256, sizeof(float) * 16 * J * J, c.st>>>(dY, C, b.G, C, b.AB, bc.Ck, J, 4, C / 4, dG,
-                                                                               C, dab, dCk);
+                                                                               C, dab, dCkp);
+    col_sum_det_kernel<<<cdiv(4 * J * J, 32), 256, 0, c.st>>>(dCkp, F, 4 * J * J, dCk);
     cudaMemsetAsync(dsum, 0, sizeof(double) * (C + 8), c.st);
     dim3 g1(cdiv(C, 32), (unsigned)std::min<long long>(256, (M + 7) / 8));
     col_sum_kernel<<<g1, 256, 0, c.st>>>(dG, M, C, C, dsum);

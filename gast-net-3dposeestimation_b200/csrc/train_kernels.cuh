@@ -467,11 +467,30 @@ __global__ void att_mix_fwd_kernel(const float* __restrict__ G, int ldg, const f
   }
 }
 
-// adjoint: dG, dab, dCk (dCk accumulated over frames with atomics)
+// out[n] = sum_m X[m][n] in a FIXED order (block = 32 columns x 8 row lanes, every lane walks its rows in order, the
+// lanes are added in order): run-to-run reproducible, unlike atomics.  Used for dC_k: its float atomics were the only
+// run-to-run difference of the whole training step (tools/train_determinism.py), and Adam(amsgrad) amplifies a 1e-8
+// difference in one gradient into +-lr differences of 3-15 % of the parameters within three steps.
+__global__ void col_sum_det_kernel(const float* __restrict__ X, long long M, int N, float* __restrict__ out) {
+  __shared__ double sh[8][33];
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  double s = 0.0;
+  if (n < N)
+    for (long long m = rl; m < M; m += 8) s += (double)X[m * N + n];
+  sh[rl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (rl == 0 && n < N) {
+    for (int i = 1; i < 8; ++i) s += sh[i][threadIdx.x & 31];
+    out[n] = (float)s;
+  }
+}
+
+// adjoint: dG, dab, and this frame's contribution to dCk (dCk_part[f][H*J*J], summed over the frames by col_sum_det_kernel)
 __global__ void att_mix_bwd_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ G, int ldg,
                                    const float* __restrict__ ab, const float* __restrict__ ck, int J, int H, int Cg,
                                    float* __restrict__ dG, int lddg, float* __restrict__ dab,
-                                   float* __restrict__ dCk) {
+                                   float* __restrict__ dCk_part) {
   extern __shared__ float sm[];            // P[H][J][J], att[H][J][J], datt[H][J][J], lin[H][J][J]
   const long long f = blockIdx.x;
   const int H2 = 2 * H, JJ = J * J;
@@ -507,7 +526,7 @@ __global__ void att_mix_bwd_kernel(const float* __restrict__ dY, int lddy, const
     for (int c = 0; c < Cg; ++c)
       s = fmaf(dY[(f * J + i) * lddy + h * Cg + c], G[(f * J + j) * ldg + h * Cg + c], s);
     datt[t] = s;
-    atomicAdd(dCk + t, s);
+    dCk_part[f * (long long)(H * JJ) + t] = s;
   }
   // dG[j,n] = sum_i att[h][i][j] dY[i,n]
   const int Ng = H * Cg;

@@ -111,8 +111,27 @@ def main():
             stats('K=%4d %-8s tcgen05 hi.hi vs exact(hi.hi)' % (K, kind), gemm(Ah, Wh, 0, 0), refh)
 
 
+def train_perf():
+    """FFMA vs tcgen05 3xTF32 on the GEMM shapes of a b = 128 training step (forward / dgrad)"""
+    rs = np.random.RandomState(2)
+    for (M, N, K) in ((19584, 512, 128), (19584, 256, 384), (6528, 1024, 256), (6528, 512, 768), (6528, 256, 768),
+                      (2176, 2048, 512), (2176, 1024, 1536), (2176, 512, 1536), (2176, 1536, 1024)):
+        a = torch.from_numpy(rs.standard_normal((M, K)).astype(np.float32)).cuda()
+        w = torch.from_numpy(rs.standard_normal((N, K)).astype(np.float32)).cuda()
+        o = torch.empty((M, N), dtype=torch.float32, device='cuda')
+        line = 'M=%d N=%d K=%d |' % (M, N, K)
+        for core, name in ((1, 'ffma'), (2, 'tc 3xTF32'), (0, 'tc tf32+bf16')):
+            ms = C.c_float(0)
+            rc = lib.gast_debug_gemm(a.data_ptr(), w.data_ptr(), o.data_ptr(), M, N, K, core, 0, 10, C.byref(ms),
+                                     torch.cuda.current_stream().cuda_stream)
+            line += ' %s %.4f ms (%.0f TF/s)' % (name, ms.value, 2e-9 * M * N * K / max(ms.value, 1e-6)) if rc == 0 else ' %s ERR' % name
+        print(line, flush=True)
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == '--perf':
+    if len(sys.argv) > 1 and sys.argv[1] == '--train':
+        train_perf()
+    elif len(sys.argv) > 1 and sys.argv[1] == '--perf':
         perf()
     else:
         main()
