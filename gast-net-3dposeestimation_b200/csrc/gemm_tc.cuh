@@ -100,6 +100,16 @@ constexpr int TC_CONV_PIPE = GAST_TC_CONV_PIPE;
 #endif
 constexpr int TC_DUAL_ISSUE = GAST_TC_DUAL_ISSUE;
 constexpr int TC_NISSUE = TC_DUAL_ISSUE ? 2 : 1;
+#ifndef GAST_TC_CG_DEFAULT
+#define GAST_TC_CG_DEFAULT 2
+#endif
+#ifndef GAST_TC_REMOTE_RELEASE_CLUSTER
+#define GAST_TC_REMOTE_RELEASE_CLUSTER 0
+#endif
+#ifndef GAST_TC_CG2_DEEP
+#define GAST_TC_CG2_DEEP 1
+#endif
+constexpr int TC_CG_DEFAULT = GAST_TC_CG_DEFAULT;   // 2 = CTA-pair MMAs (tcgen05 cta_group::2) unless GAST_TC_CG says otherwise
 
 
 constexpr int TC_EN = 64;         // accumulator columns owned by one epilogue warpgroup
@@ -119,7 +129,7 @@ constexpr int TC_OFF_AB = TC_OFF_STAGING + TC_EPI_BYTES;
 constexpr int TC_OFF_XPOSE = (TC_OFF_AB + 128 * 8 * 4 + 1023) / 1024 * 1024;  // raw A ring (1024-aligned: TMA SWIZZLE_128B)
 constexpr int TC_OFF_BAR = TC_OFF_XPOSE + TC_RSTAGES * 128 * TC_XLD * 4;
 static_assert(TC_OFF_STAGING % 1024 == 0 && TC_OFF_XPOSE % 1024 == 0, "swizzled regions must be 1024-byte aligned");
-constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 384 + 1024;
+constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 512 + 1024;
 static_assert(TC_SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");   // 26 mbarriers + tmem ptr, + alignment slack
 
 // ----------------------------------------------------------------------------------------
@@ -194,6 +204,62 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ---- cta_group::2 (CTA pair) forms.  All tcgen05 instructions of one kernel use the same cta_group, so these are
+// selected by the kernel's CG template parameter.
+// shared::cluster address of `addr` (a shared::cta address of this CTA's window) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// arrive on an mbarrier of any CTA of the cluster (shared::cluster address from mapa_u32)
+// (default semantics = release at CTA scope, like the local arrives: the hand-over it signals is a tensor-memory
+//  write / read ordered by tcgen05.fence, not generic-proxy memory.  The .release.cluster form measured 2x slower
+//  kernels: every converter warp paid a cluster-scope fence per chunk, profiles/r02_tc_attribution.md #16.)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+#if GAST_TC_REMOTE_RELEASE_CLUSTER
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
+}
+// TMA load whose bytes are counted on an mbarrier of ANOTHER CTA of the pair (`bar` is a shared::cluster address):
+// both CTAs load their half of the B tile into their own shared memory and signal the MMA-issuing CTA's barrier
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs, 128 rows each] (+)= A[tmem of each CTA] . B[64 rows from each CTA's smem]^T : M = 256, N = 128
+__device__ __forceinline__ void umma_tf32_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// completion of this thread's earlier MMAs -> the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc2(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
@@ -336,6 +402,11 @@ constexpr uint32_t TC_A_COL = 256;
 // instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=128
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
                               ((uint32_t)(TC_BM >> 4) << 24);
+// cta_group::2: M = 256 over the CTA pair (128 rows in each CTA's tensor memory)
+constexpr uint32_t TC_IDESC2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                               ((uint32_t)((2 * TC_BM) >> 4) << 24);
+constexpr uint32_t TC_IDESC2_BF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                                  ((uint32_t)((2 * TC_BM) >> 4) << 24);
 // the same with A=B=bf16 (kind::f16 format code 1), for the correction products
 constexpr uint32_t TC_IDESC_BF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
                                  ((uint32_t)(TC_BM >> 4) << 24);
@@ -365,7 +436,18 @@ struct TcGroupOf {
 // noise (tests/test_gpu_train.py), which the bf16 corrections would exceed.  Same rings, barriers and tensor-memory map:
 // the 32 "pair" columns of an A stage hold 32 fp32 lo values instead of 16 + 16 bf16 pairs, the second 16 KB of a B
 // stage the fp32 lo tile instead of the bf16 [hi | lo] rows.
-template <int EPI, int DBG = 0, int PREC = 0>
+// CG: 1 = every CTA issues its own M = 128 MMAs and the two CTAs of a cluster multicast the B tile to each other;
+// 2 = CTA PAIR (tcgen05 cta_group::2): the rank-0 CTA issues M = 256 MMAs for both -- each CTA converts its own 128 rows
+// of A into its own tensor memory and accumulates its own 128 rows, but loads only ITS HALF of the B tile (64 of the
+// 128 weight rows) into its shared memory; the tensor cores of the pair read both halves.  Per CTA and chunk that is
+// 16 KB instead of 32 KB of TMA writes and 16 KB instead of 32 KB of operand reads: at M = N = 128 the shared-memory
+// port (TMA writes of A and B + MMA reads of B + the converters' reads of A = 96 KB per ~1000-cycle chunk at
+// 128 B/clk), not the issuing thread or the converters, is what no single-CTA variant could get past
+// (profiles/r02_tc_attribution.md, experiments 10-13).  Protocol differences: the operand "full" barriers and the
+// accumulator "empty" barriers that the issuer waits on live in the rank-0 CTA and collect arrivals from both CTAs
+// (remote mbarrier arrives; the peer's B TMA counts its bytes on the leader's barrier), every commit is multicast to
+// both CTAs.
+template <int EPI, int DBG = 0, int PREC = 0, int CG = 1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap amap0,
@@ -391,8 +473,14 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
   // The operand "full" barriers exist once per issuing warp: the issuer of a chunk's flush group is the only
   // waiter of that barrier instance, so it sees EVERY phase of it (an mbarrier parity wait cannot tell a phase
   // from the one two later, which an issuer that skips the other issuer's chunks would otherwise run into).
-  constexpr uint32_t BB_FULL = 0, BB_EMPTY = 64, BA_FULL = 96, BA_EMPTY = 160, BM_FULL = 192, BM_EMPTY = 208,
-                     B_TMEMPTR = 224, BR_FULL = 256, BR_EMPTY = 288;
+  // CTA pair: a B stage holds this CTA's 64 weight rows only (8 KB hi + 8 KB pk), so the same 96 KB give a ring of
+  // twice the depth -- the operand round trip now includes a remote complete_tx and a multicast commit
+  constexpr int BST = (CG == 2 && GAST_TC_CG2_DEEP) ? 2 * TC_BSTAGES : TC_BSTAGES;        // B stages
+  constexpr int BSB = (CG == 2 && GAST_TC_CG2_DEEP) ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES; // bytes per B stage
+  constexpr int BPK = (CG == 2 && GAST_TC_CG2_DEEP) ? 8192 : 16384;                        // offset of the pk / lo half
+  constexpr uint32_t BB_FULL = (BST > 4) ? 320 : 0, BB_EMPTY = (BST > 4) ? 320 + 16 * BST : 64, BA_FULL = 96, BA_EMPTY = 160,
+                     BM_FULL = 192, BM_EMPTY = 208, B_TMEMPTR = 224, BR_FULL = 256, BR_EMPTY = 288;
+  static_assert(320 + 24 * BST <= 512, "barrier area");
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + TC_OFF_BAR + B_TMEMPTR);
   constexpr uint32_t NMAIN = TC_NMAIN;
 
@@ -408,18 +496,19 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
   const int cid = blockIdx.x / TC_CLUSTER, ncl = gridDim.x / TC_CLUSTER;
   auto tile_f0 = [&](int q) { return (TC_CLUSTER * (q / n_tiles_n) + (int)crank) * p.fpt; };
 
+  static_assert(CG == 1 || (TC_CLUSTER == 2 && !TC_DUAL_ISSUE && (DBG == 0 || DBG == 4 || DBG == 5 || DBG == 8 || DBG == 9)), "the CTA-pair form needs 2-CTA clusters");
   if (tid == 0) {
-    for (int s = 0; s < TC_BSTAGES; ++s) {
+    for (int s = 0; s < BST; ++s) {
       for (int q = 0; q < 2; ++q) mbar_init(bar0 + BB_FULL + 8 * (2 * s + q), 1);     // expect_tx arrive + TMA bytes
-      mbar_init(bar0 + BB_EMPTY + 8 * s, TC_CLUSTER);   // tcgen05.commit of every CTA of the cluster
+      mbar_init(bar0 + BB_EMPTY + 8 * s, CG == 2 ? 1 : TC_CLUSTER);   // tcgen05.commit of every issuing CTA of the cluster
     }
     for (int s = 0; s < TC_ASTAGES; ++s) {
-      for (int q = 0; q < 2; ++q) mbar_init(bar0 + BA_FULL + 8 * (2 * s + q), 4);     // 4 A-producer warps
+      for (int q = 0; q < 2; ++q) mbar_init(bar0 + BA_FULL + 8 * (2 * s + q), 4 * CG);     // 4 A-producer warps (of each CTA of the pair)
       mbar_init(bar0 + BA_EMPTY + 8 * s, 1);    // tcgen05.commit
     }
     for (int b = 0; b < (int)NMAIN; ++b) {
       mbar_init(bar0 + BM_FULL + 8 * b, 1);     // tcgen05.commit
-      mbar_init(bar0 + BM_EMPTY + 8 * b, 8);    // 8 accumulate/epilogue warps (two column groups)
+      mbar_init(bar0 + BM_EMPTY + 8 * b, 8 * CG);    // 8 accumulate/epilogue warps (two column groups) (of each CTA of the pair)
     }
     for (int r = 0; r < TC_RSTAGES; ++r) {
       mbar_init(bar0 + BR_FULL + 8 * r, 1);     // raw A slot: expect_tx arrive + TMA bytes
@@ -427,12 +516,14 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) tmem_alloc(sbase + TC_OFF_BAR + B_TMEMPTR, 512);
+  if (warp == 9) { if (CG == 2) tmem_alloc2(sbase + TC_OFF_BAR + B_TMEMPTR, 512); else tmem_alloc(sbase + TC_OFF_BAR + B_TMEMPTR, 512); }
   tc_fence_before();
   __syncthreads();
   if (TC_CLUSTER > 1) cluster_sync_all();   // peer barriers initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  // CTA pair: the barriers the MMA issuer waits on are the rank-0 CTA's (shared::cluster addresses for remote arrives)
+  const uint32_t lead_bar0 = (CG == 2) ? mapa_u32(bar0, 0) : bar0;
 
   int nchunks = 0;
   for (int s = 0; s < p.nseg; ++s) nchunks += p.seg[s].K / TC_BK;
@@ -605,7 +696,10 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar0 + BA_FULL + 8 * (2 * stage + gof.role()));
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(lead_bar0 + BA_FULL + 8 * (2 * stage + gof.role()));
+          else mbar_arrive(bar0 + BA_FULL + 8 * (2 * stage + gof.role()));
+        }
         gof.next(nchunks);
         if (++stage == TC_ASTAGES) { stage = 0; phase ^= 1; }
       }
@@ -668,7 +762,10 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar0 + BA_FULL + 8 * (2 * stage + gof.role()));
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(lead_bar0 + BA_FULL + 8 * (2 * stage + gof.role()));
+        else mbar_arrive(bar0 + BA_FULL + 8 * (2 * stage + gof.role()));
+      }
       gof.next(nchunks);
       if (DBG == 6) tA_st += clock64() - t0;
       if (++stage == TC_ASTAGES) { stage = 0; phase ^= 1; }
@@ -699,8 +796,19 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           if (DBG == 6) tB_wait += clock64() - t0;
           const uint32_t full = bar0 + BB_FULL + 8 * (2 * stage + gof.role());
           if (DBG == 8 || DBG == 9) {                            // experiment: MMAs on stale smem, no B traffic
-            mbar_arrive(full);
-            if (++stage == TC_BSTAGES) { stage = 0; phase ^= 1; }
+            if (CG == 1 || crank == 0) mbar_arrive(full);
+            if (++stage == BST) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          if (CG == 2) {
+            // CTA pair: this CTA's 64 weight rows (hi and pk) into ITS shared memory; the bytes of both CTAs are counted
+            // on the rank-0 CTA's barrier, which its issuer waits on
+            if (crank == 0) mbar_arrive_expect_tx(full, 2 * 16384);
+            const uint32_t dst = sbase + stage * BSB;
+            const uint32_t lfull = lead_bar0 + BB_FULL + 8 * (2 * stage + gof.role());
+            tma_load_2d_cg2(dst, &map_hi, lfull, c * TC_BK, n0 + (TC_BN / 2) * (int)crank);
+            tma_load_2d_cg2(dst + BPK, &map_lo, lfull, (PREC == 1 ? 1 : 2) * c * TC_BK, n0 + (TC_BN / 2) * (int)crank);
+            if (++stage == BST) { stage = 0; phase ^= 1; }
             continue;
           }
           mbar_arrive_expect_tx(full, 2 * 16384);                // own share + the peers' shares
@@ -830,8 +938,8 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       if (DBG == 6 && p.dbg && lane == 0 && role == 0)
         for (int i = 0; i < 5; ++i) p.dbg[(size_t)blockIdx.x * 32 + 16 + i] = (unsigned long long)tM[i];
     }
-    } else if (warp == 9) {
-    // ================================================================= MMA issuer
+    } else if (warp == 9 && (CG == 1 || crank == 0)) {
+    // ================================================================= MMA issuer (CTA pair: of the rank-0 CTA only)
     // The whole warp runs this loop converged so that descriptors and barrier addresses live in
     // uniform registers; one elected lane issues.  (Issuing from inside `if (lane == 0)` made
     // every tcgen05.mma pay a ~55-cycle vector->uniform waterfall: 824 cycles per chunk for a
@@ -860,13 +968,13 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           tc_fence_after();
           const uint32_t d_main = tmem_base + mb * TC_BN;
           const uint32_t a_hi = tmem_base + TC_A_COL + as * 64, a_pk = a_hi + 32;
-          const uint32_t sb = sbase + bs * TC_STAGE_BYTES;
-          const uint64_t b_hi = make_smem_desc(sb), b_pk = make_smem_desc(sb + 16384);
+          const uint32_t sb = sbase + bs * BSB;
+          const uint64_t b_hi = make_smem_desc(sb), b_pk = make_smem_desc(sb + BPK);
           const bool last_of_group = (cg == TC_FLUSH - 1 || c == nchunks - 1);
           // ring positions of the next chunk (same rings across tile boundaries)
-          const int as_n = (as + 1 == TC_ASTAGES) ? 0 : as + 1, bs_n = (bs + 1 == TC_BSTAGES) ? 0 : bs + 1;
+          const int as_n = (as + 1 == TC_ASTAGES) ? 0 : as + 1, bs_n = (bs + 1 == BST) ? 0 : bs + 1;
           const uint32_t aph_n = (as + 1 == TC_ASTAGES) ? (aphase ^ 1) : aphase;
-          const uint32_t bph_n = (bs + 1 == TC_BSTAGES) ? (bphase ^ 1) : bphase;
+          const uint32_t bph_n = (bs + 1 == BST) ? (bphase ^ 1) : bphase;
           // ONE elected block per chunk: every elect.sync + reconvergence costs ~50 cycles of this thread, and the
           // thread's instruction stream, not the tensor pipe, paces the chunk rate (8 MMAs execute in ~500 cycles,
           // the loop body took ~700 with one elected block per k-step: profiles/r02_tc_attribution.md).  The probes
@@ -875,6 +983,16 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
 #pragma unroll
             for (int k = 0; k < TC_BK / 8; ++k) {
               const uint64_t adv = (uint64_t)(k * 2);      // 8 fp32 = 32 B = 2 x 16 B
+              if (CG == 2) {
+                umma_tf32_ts2(d_main, a_hi + 8 * k, b_hi + adv, TC_IDESC2, (cg | k) ? 1u : 0u);
+                if (PREC == 1) {
+                  umma_tf32_ts2(d_main, a_pk + 8 * k, b_hi + adv, TC_IDESC2, 1u);
+                  umma_tf32_ts2(d_main, a_hi + 8 * k, b_pk + adv, TC_IDESC2, 1u);
+                } else {
+                  umma_bf16_ts2(d_main, a_pk + 8 * k, b_pk + adv, TC_IDESC2_BF, 1u);
+                }
+                continue;
+              }
               if (DBG != 7) umma_tf32_ts(d_main, a_hi + 8 * k, b_hi + adv, TC_IDESC, (cg | k) ? 1u : 0u);
               if (PREC == 1) {                  // 3xTF32: A_lo.B_hi and A_hi.B_lo as tf32 products of their own
                 umma_tf32_ts(d_main, a_pk + 8 * k, b_hi + adv, TC_IDESC, 1u);
@@ -885,10 +1003,16 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
               // tf32 MMAs first and the four bf16 ones after them measured 5 % slower than interleaving them.)
               if (DBG != 3) umma_bf16_ts(d_main, a_pk + 8 * k, b_pk + adv, TC_IDESC_BF, (DBG == 7 && !(cg | k)) ? 0u : 1u);
             }
+            if (CG == 2) {                                  // every release goes to both CTAs of the pair
+              umma_commit_mc2(bar0 + BB_EMPTY + 8 * bs, (uint16_t)3);
+              umma_commit_mc2(bar0 + BA_EMPTY + 8 * as, (uint16_t)3);
+              if (last_of_group) umma_commit_mc2(bar0 + BM_FULL + 8 * mb, (uint16_t)3);
+            } else {
             if (TC_CLUSTER > 1) umma_commit_mc(bar0 + BB_EMPTY + 8 * bs, (uint16_t)((1u << TC_CLUSTER) - 1));
             else umma_commit(bar0 + BB_EMPTY + 8 * bs);     // frees the B smem stage when the MMAs retire
             umma_commit(bar0 + BA_EMPTY + 8 * as);          // frees the A tmem stage
             if (last_of_group) umma_commit(bar0 + BM_FULL + 8 * mb);   // group sum ready
+            }
           }
           __syncwarp();
           pre_a = mbar_try(bar0 + BA_FULL + 16 * as_n, aph_n);
@@ -1015,7 +1139,10 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar0 + BM_EMPTY + 8 * mb);
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(lead_bar0 + BM_EMPTY + 8 * mb);
+          else mbar_arrive(bar0 + BM_EMPTY + 8 * mb);
+        }
         ++mcount;
         if (DBG == 6) tE_fl += clock64() - t0;
       }
@@ -1041,7 +1168,10 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar0 + BM_EMPTY + 8 * mb);
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(lead_bar0 + BM_EMPTY + 8 * mb);
+          else mbar_arrive(bar0 + BM_EMPTY + 8 * mb);
+        }
         ++mcount;
       }
       if (DBG == 6) ++tE_tiles;
@@ -1289,7 +1419,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
   if (TC_CLUSTER > 1) cluster_sync_all();   // peers may multicast into / arrive on this CTA until they finish
   if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (CG == 2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
   (void)0;
 }
@@ -1466,7 +1596,7 @@ inline void tc_build_amaps(GemmP& p, TcAMaps& am) {
   p.a_tma = am.ok ? 1 : 0;
 }
 
-template <int EPI, int DBG, int PREC = 0>
+template <int EPI, int DBG, int PREC = 0, int CG = 1>
 inline int tc_launch_one(int grid, cudaStream_t st, const GemmP& p_in, const TcWeights& t, int nt, int items) {
   GemmP p = p_in;
   TcAMaps am;
@@ -1476,7 +1606,7 @@ inline int tc_launch_one(int grid, cudaStream_t st, const GemmP& p_in, const TcW
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)gemm_tc_kernel<EPI, DBG, PREC>,
+    cudaError_t e = cudaFuncSetAttribute((const void*)gemm_tc_kernel<EPI, DBG, PREC, CG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set[dev & 63] = true;
@@ -1493,7 +1623,7 @@ inline int tc_launch_one(int grid, cudaStream_t st, const GemmP& p_in, const TcW
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return (int)cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, DBG, PREC>, p, t.map_hi, t.map_lo, am.m[0], am.m[1], am.m[2], nt, items);
+  return (int)cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, DBG, PREC, CG>, p, t.map_hi, t.map_lo, am.m[0], am.m[1], am.m[2], nt, items);
 }
 
 inline int tc_launch(int sm_count, cudaStream_t st, int epi, const GemmP& p, const TcWeights& t, int dbg = 0) {
@@ -1503,10 +1633,28 @@ inline int tc_launch(int sm_count, cudaStream_t st, int epi, const GemmP& p, con
   if (items > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
   const int max_cl = sm_count / TC_CLUSTER;
   const int grid = TC_CLUSTER * (int)(items < max_cl ? items : max_cl);
+  // CTA-pair form (cta_group::2): GAST_TC_CG=1 selects the single-CTA MMAs with B multicast (A/B runs)
+  static const int cg = (TC_CLUSTER == 2 && !TC_DUAL_ISSUE) ? (getenv("GAST_TC_CG") ? atoi(getenv("GAST_TC_CG")) : TC_CG_DEFAULT) : 1;
   if (t.prec == 1) {                       // 3xTF32 (training): plain epilogue only
     if (epi != EPI_PLAIN || dbg) return (int)cudaErrorInvalidValue;
+#if GAST_TC_CLUSTER == 2 && !GAST_TC_DUAL_ISSUE
+    if (cg == 2) return tc_launch_one<EPI_PLAIN, 0, 1, 2>(grid, st, p, t, nt, (int)items);
+#endif
     return tc_launch_one<EPI_PLAIN, 0, 1>(grid, st, p, t, nt, (int)items);
   }
+#if GAST_TC_CLUSTER == 2 && !GAST_TC_DUAL_ISSUE
+  if (cg == 2 && !dbg) {
+    if (epi == EPI_PLAIN) return tc_launch_one<EPI_PLAIN, 0, 0, 2>(grid, st, p, t, nt, (int)items);
+    if (epi == EPI_SEMCH) return tc_launch_one<EPI_SEMCH, 0, 0, 2>(grid, st, p, t, nt, (int)items);
+    return tc_launch_one<EPI_GLOBAL, 0, 0, 2>(grid, st, p, t, nt, (int)items);
+  }
+#endif
+#if GAST_TC_CLUSTER == 2 && !GAST_TC_DUAL_ISSUE
+  if (cg == 2 && dbg == 4) return tc_launch_one<EPI_PLAIN, 4, 0, 2>(grid, st, p, t, nt, (int)items);
+  if (cg == 2 && dbg == 5) return tc_launch_one<EPI_PLAIN, 5, 0, 2>(grid, st, p, t, nt, (int)items);
+  if (cg == 2 && dbg == 8) return tc_launch_one<EPI_PLAIN, 8, 0, 2>(grid, st, p, t, nt, (int)items);
+  if (cg == 2 && dbg == 9) return tc_launch_one<EPI_PLAIN, 9, 0, 2>(grid, st, p, t, nt, (int)items);
+#endif
   if (dbg) {
     if (epi != EPI_PLAIN) return (int)cudaErrorInvalidValue;
     switch (dbg) {

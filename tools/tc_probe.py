@@ -128,8 +128,27 @@ def train_perf():
         print(line, flush=True)
 
 
+def cg_perf():
+    """full kernel / MMAs without operand traffic / MMAs + barrier hand-shakes only, for the cta_group selected by GAST_TC_CG"""
+    rs = np.random.RandomState(1)
+    print('GAST_TC_CG=%s' % os.environ.get('GAST_TC_CG', 'default'))
+    for (M, N, K) in ((75008, 1024, 1536), (224768, 512, 768), (674176, 128, 128)):
+        a = torch.from_numpy(rs.standard_normal((M, K)).astype(np.float32)).cuda()
+        w = torch.from_numpy(rs.standard_normal((N, K)).astype(np.float32)).cuda()
+        o = torch.empty((M, N), dtype=torch.float32, device='cuda')
+        line = 'M=%d N=%d K=%d |' % (M, N, K)
+        for mode, name in ((0, 'tc'), (4, 'noSTTM'), (5, 'mma+B only'), (8, 'mma-only(no A/B traffic)'), (9, 'mma+barriers only')):
+            ms = C.c_float(0)
+            rc = lib.gast_debug_gemm(a.data_ptr(), w.data_ptr(), o.data_ptr(), M, N, K, 0, mode, 5, C.byref(ms),
+                                     torch.cuda.current_stream().cuda_stream)
+            line += ' %s %.3f' % (name, ms.value) if rc == 0 else ' %s ERR(%s)' % (name, _lib.last_error()[:40])
+        print(line, flush=True)
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == '--train':
+    if len(sys.argv) > 1 and sys.argv[1] == '--cg':
+        cg_perf()
+    elif len(sys.argv) > 1 and sys.argv[1] == '--train':
         train_perf()
     elif len(sys.argv) > 1 and sys.argv[1] == '--perf':
         perf()
