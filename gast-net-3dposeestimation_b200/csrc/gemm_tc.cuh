@@ -11,12 +11,15 @@
 // 4 (tf32) + 4 (bf16) tensor-pipe slots instead of the 12 of 3xTF32 (round 1).  Same tiles,
 // A-gather and fused epilogues as gemm_ffma.cuh, so both cores are interchangeable per launch.
 //
-// Persistent, warp-specialised CTA (one per SM, 2-CTA clusters share the B tile), 512 threads, registers
-// re-balanced with setmaxnreg (152 / 160 / 40 / 160):
+// Persistent, warp-specialised CTA (one per SM), launched as 2-CTA clusters that work as a CTA PAIR (tcgen05 cta_group::2,
+// template parameter CG = 2): adjacent M tiles, same N tile; the rank-0 CTA issues M = 256 MMAs for both, each CTA loads
+// only its half of the B tile (see the comment at the kernel).  512 threads, registers re-balanced with setmaxnreg
+// (136 / 168 / 40 / 168):
 //   warps 0-3   A converters : raw A rows (TMA or cp.async ring in smem) -> hi (tf32) | packed bf16 [lo | hi] ->
 //                              tcgen05.st into the A ring in TENSOR memory (TS-form MMA)
-//   warp  8     B producer   : TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B, cluster multicast) of the pre-split weights
-//   warp  9     MMA issuer   : one elected thread issues tcgen05.mma.kind::tf32, accumulators in TMEM
+//   warp  8     B producer   : TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) of this CTA's 64 rows of the pre-split weights,
+//                              bytes counted on the rank-0 CTA's barrier (CG = 1: whole tile, multicast across the cluster)
+//   warp  9     MMA issuer   : one elected thread (of the rank-0 CTA) issues tcgen05.mma kind::tf32 / kind::f16, accumulators in TMEM
 //   warp  10    A producer   : TMA (cp.async.bulk.tensor.3d) of the raw A tile when the frame map is affine
 //   warps 4-7   accumulate + epilogue of accumulator columns 0-63
 //   warps 12-15 accumulate + epilogue of accumulator columns 64-127
@@ -61,7 +64,16 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;
 #define GAST_TC_RSTAGES 4
 #endif
 constexpr int TC_BSTAGES = GAST_TC_BSTAGES;   // B (weights) ring in shared memory, filled by TMA
-constexpr int TC_RSTAGES = GAST_TC_RSTAGES;   // raw A ring in shared memory, filled by TMA or cp.async (no register staging, no MSHR cap)
+constexpr int TC_RSTAGES = GAST_TC_RSTAGES;   // raw A ring in shared memory, filled by cp.async (no register staging, no MSHR cap)
+// ... and when it is filled by TMA (16 KB per slot): the bytes in flight per SM bound the chunk rate -- 4 slots = 64 KB
+// against ~3500 cycles of load latency under load = 18 B/clk = one 16 KB chunk per ~880 cycles, the measured period of
+// the CTA-pair kernel -- so the shared memory the CTA pair frees (half a B tile per CTA) goes into this ring
+#ifndef GAST_TC_RSTAGES_TMA
+#define GAST_TC_RSTAGES_TMA 4
+#endif
+constexpr int TC_RSTAGES_TMA = GAST_TC_RSTAGES_TMA;
+constexpr int TC_RAW_BYTES = (TC_RSTAGES * 128 * 36 * 4 > TC_RSTAGES_TMA * 16384) ? TC_RSTAGES * 128 * 36 * 4 : TC_RSTAGES_TMA * 16384;
+static_assert(TC_RSTAGES <= 8 && TC_RSTAGES_TMA <= 8, "8 raw-slot barriers");
 #ifndef GAST_TC_ASTAGES
 #define GAST_TC_ASTAGES 4
 #endif
@@ -89,6 +101,9 @@ static_assert(TC_REG_A + 2 * TC_REG_E + TC_REG_M <= 512, "register file over-sub
 #define GAST_TC_CONV_PIPE 1
 #endif
 constexpr int TC_CONV_PIPE = GAST_TC_CONV_PIPE;
+#ifndef GAST_TC_CONV_ST_EARLY
+#define GAST_TC_CONV_ST_EARLY 1
+#endif
 #ifndef GAST_TC_TRUNC_SPLIT
 #define GAST_TC_TRUNC_SPLIT 0
 #endif
@@ -127,7 +142,8 @@ constexpr int TC_EPI_BYTES = 2 * 128 * TC_XLD * 4 + TC_MAX_NNZ * TC_SLD * 4;
 constexpr int TC_OFF_STAGING = TC_BSTAGES * TC_STAGE_BYTES;
 constexpr int TC_OFF_AB = TC_OFF_STAGING + TC_EPI_BYTES;
 constexpr int TC_OFF_XPOSE = (TC_OFF_AB + 128 * 8 * 4 + 1023) / 1024 * 1024;  // raw A ring (1024-aligned: TMA SWIZZLE_128B)
-constexpr int TC_OFF_BAR = TC_OFF_XPOSE + TC_RSTAGES * 128 * TC_XLD * 4;
+static_assert(TC_XLD == 36, "TC_RAW_BYTES assumes the 36-float row stride of the cp.async layout");
+constexpr int TC_OFF_BAR = TC_OFF_XPOSE + TC_RAW_BYTES;
 static_assert(TC_OFF_STAGING % 1024 == 0 && TC_OFF_XPOSE % 1024 == 0, "swizzled regions must be 1024-byte aligned");
 constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 512 + 1024;
 static_assert(TC_SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");   // 26 mbarriers + tmem ptr, + alignment slack
@@ -468,8 +484,8 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
   float* staging = reinterpret_cast<float*>(smem + TC_OFF_STAGING);
   float* ab_s = reinterpret_cast<float*>(smem + TC_OFF_AB);
   const uint32_t bar0 = sbase + TC_OFF_BAR;
-  // mbarriers (8 B each):  b_full[4 stages][2 issuers] @0  b_empty[4] @64  a_full[4][2] @96  a_empty[4] @160
-  //                        main_full[2] @192  main_empty[2] @208 ; tmem ptr @224 ; raw_full[4] @256  raw_empty[4] @288
+  // mbarriers (8 B each):  b_full[8 stages][2 issuers] @0  b_empty[8] @128  a_full[4][2] @192  a_empty[4] @256
+  //                        main_full[2] @288  main_empty[2] @304 ; tmem ptr @320 ; raw_full[8] @328  raw_empty[8] @392
   // The operand "full" barriers exist once per issuing warp: the issuer of a chunk's flush group is the only
   // waiter of that barrier instance, so it sees EVERY phase of it (an mbarrier parity wait cannot tell a phase
   // from the one two later, which an issuer that skips the other issuer's chunks would otherwise run into).
@@ -478,9 +494,9 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
   constexpr int BST = (CG == 2 && GAST_TC_CG2_DEEP) ? 2 * TC_BSTAGES : TC_BSTAGES;        // B stages
   constexpr int BSB = (CG == 2 && GAST_TC_CG2_DEEP) ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES; // bytes per B stage
   constexpr int BPK = (CG == 2 && GAST_TC_CG2_DEEP) ? 8192 : 16384;                        // offset of the pk / lo half
-  constexpr uint32_t BB_FULL = (BST > 4) ? 320 : 0, BB_EMPTY = (BST > 4) ? 320 + 16 * BST : 64, BA_FULL = 96, BA_EMPTY = 160,
-                     BM_FULL = 192, BM_EMPTY = 208, B_TMEMPTR = 224, BR_FULL = 256, BR_EMPTY = 288;
-  static_assert(320 + 24 * BST <= 512, "barrier area");
+  constexpr uint32_t BB_FULL = 0, BB_EMPTY = 128, BA_FULL = 192, BA_EMPTY = 256, BM_FULL = 288, BM_EMPTY = 304,
+                     B_TMEMPTR = 320, BR_FULL = 328, BR_EMPTY = 392;
+  static_assert(BST <= 8, "barrier area: 8 B stages");
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + TC_OFF_BAR + B_TMEMPTR);
   constexpr uint32_t NMAIN = TC_NMAIN;
 
@@ -510,7 +526,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       mbar_init(bar0 + BM_FULL + 8 * b, 1);     // tcgen05.commit
       mbar_init(bar0 + BM_EMPTY + 8 * b, 8 * CG);    // 8 accumulate/epilogue warps (two column groups) (of each CTA of the pair)
     }
-    for (int r = 0; r < TC_RSTAGES; ++r) {
+    for (int r = 0; r < 8; ++r) {
       mbar_init(bar0 + BR_FULL + 8 * r, 1);     // raw A slot: expect_tx arrive + TMA bytes
       mbar_init(bar0 + BR_EMPTY + 8 * r, 4);    // 4 A-producer warps have read it
     }
@@ -668,7 +684,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       float4 xr[8];
       if (!row_in_box) {
 #pragma unroll
-        for (int sl = 0; sl < TC_RSTAGES; ++sl) {
+        for (int sl = 0; sl < TC_RSTAGES_TMA; ++sl) {
           float4* rz = reinterpret_cast<float4*>(smem + TC_OFF_XPOSE + sl * 16384 + my_row * 128);
 #pragma unroll
           for (int i = 0; i < 8; ++i) rz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -683,22 +699,39 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         split_row(xr, hi, lo);                 // consumes every raw value: the shared-memory reads are complete
         __syncwarp();
         if (lane == 0) mbar_arrive(bar0 + BR_EMPTY + 8 * slot);   // raw slot free for the TMA producer
-        if (++slot == TC_RSTAGES) { slot = 0; rphase ^= 1; }
-        if (c + 1 < my_chunks) {               // next chunk's rows on their way while this one is handed over
+        if (++slot == TC_RSTAGES_TMA) { slot = 0; rphase ^= 1; }
+        const bool more = c + 1 < my_chunks;
+        bool got_next = false;
+#if !GAST_TC_CONV_ST_EARLY
+        if (more) {                            // next chunk's rows on their way while this one is handed over
           mbar_wait(bar0 + BR_FULL + 8 * slot, rphase);
           load_raw(slot, xr);
+          got_next = true;
         }
+#endif
         mbar_wait(bar0 + BA_EMPTY + 8 * stage, phase ^ 1);
         tc_fence_after();
         const uint32_t ta = tmem_base + lane_off + TC_A_COL + stage * 64;
         tmem_st32(ta, hi);
         tmem_st32(ta + 32, lo);
+#if GAST_TC_CONV_ST_EARLY
+        // the tensor-memory stores are in flight: request the next chunk's rows in their shadow (only if they have
+        // landed -- a late TMA must not hold back the hand-over of a chunk that is already converted)
+        if (more && __all_sync(0xffffffffu, mbar_try(bar0 + BR_FULL + 8 * slot, rphase))) {
+          load_raw(slot, xr);
+          got_next = true;
+        }
+#endif
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           if (CG == 2) mbar_arrive_cluster(lead_bar0 + BA_FULL + 8 * (2 * stage + gof.role()));
           else mbar_arrive(bar0 + BA_FULL + 8 * (2 * stage + gof.role()));
+        }
+        if (more && !got_next) {
+          mbar_wait(bar0 + BR_FULL + 8 * slot, rphase);
+          load_raw(slot, xr);
         }
         gof.next(nchunks);
         if (++stage == TC_ASTAGES) { stage = 0; phase ^= 1; }
@@ -769,7 +802,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       gof.next(nchunks);
       if (DBG == 6) tA_st += clock64() - t0;
       if (++stage == TC_ASTAGES) { stage = 0; phase ^= 1; }
-      if (++slot == TC_RSTAGES) { slot = 0; rphase ^= 1; }
+      if (++slot == (atma ? TC_RSTAGES_TMA : TC_RSTAGES)) { slot = 0; rphase ^= 1; }
     }
     if (!atma) cp_async_wait<0>();
     if (DBG == 6 && tid == 0 && p.dbg) {
@@ -850,14 +883,14 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
             const uint32_t full = bar0 + BR_FULL + 8 * slot;
             if (DBG == 8 || DBG == 9) {                      // experiment: no A traffic
               mbar_arrive(full);
-              if (++slot == TC_RSTAGES) { slot = 0; rphase ^= 1; }
+              if (++slot == TC_RSTAGES_TMA) { slot = 0; rphase ^= 1; }
               continue;
             }
             mbar_arrive_expect_tx(full, bytes);
             // box {32 channels, J joints, fpt frames} -> fpt*J dense 128-byte rows, swizzled;
             // frames past the end of the tensor are zero-filled (ragged last tile, dummy tiles)
             tma_load_3d(sbase + TC_OFF_XPOSE + slot * 16384, mp, full, k0 - tap * Kc, 0, f0);
-            if (++slot == TC_RSTAGES) { slot = 0; rphase ^= 1; }
+            if (++slot == TC_RSTAGES_TMA) { slot = 0; rphase ^= 1; }
           }
         }
       }
