@@ -1085,19 +1085,47 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
     long long tE_n = 0, tE_wait = 0, tE_tot = clock64(), tE_tiles = 0, tE_cw = 0, tE_cl = 0, tE_fl = 0;
     const uint32_t lane_off = ((uint32_t)(ew * 32) << 16) + (uint32_t)(eh * TC_EN);
     float* scratch = staging;                // TC_EPI_BYTES, laid out per epilogue kind below
-    // SemCH: neighbour list of this thread's joint for both masks: bits 0-7 first coefficient row,
-    // 8-11 degree (<= TC_MAXDEG, checked by tc_supported), then 5 bits per neighbour joint
-    unsigned long long nbr_pk0 = 0, nbr_pk1 = 0;
+    // SemCH tables of this thread (built once per kernel), for both masks:
+    //   sA[m]: bits 0-3 degree of this thread's joint (<= TC_MAXDEG, checked by tc_supported), bit 4 "neighbour 0 is the
+    //          joint itself", then 5 bits per neighbour joint.  The joint itself is moved to the FRONT of its list: its
+    //          term comes from registers (X.W0 of the same row), so no staged row is read for it.
+    //   sB[m]: 6 bits per neighbour k: the row of the coefficient slab that holds coef(ji, k).  The slab is k-major --
+    //          neighbour 0 of every joint, then neighbour 1 of every joint that has one, ... -- so the 8 consecutive
+    //          joints of a quarter warp read 8 consecutive rows: conflict-free.  (In the CSR order of the parameter the
+    //          rows of a quarter warp are deg(j) apart and collided: 2.1 wavefronts per ideal one,
+    //          profiles/r02_w_lines_semch1.txt; the self rows were another 40 % of the staged-row reads.)
+    //   lz   : byte (4 m + u): the CSR nonzero that belongs into slab row (et + 128 u) / 8, 0xff = none -- this thread's
+    //          (up to 4) float4 slots of the per-tile coefficient load
+    unsigned long long sA0 = 0, sA1 = 0, sB0 = 0, sB1 = 0, lz = ~0ull;
     if (EPI == EPI_SEMCH) {
 #pragma unroll
       for (int m = 0; m < 2; ++m) {
-        unsigned long long pk = 0;
-        if (p.coef[m]) {
-          const int z0 = p.nbr[m].row_ptr[ji], z1 = p.nbr[m].row_ptr[ji + 1];
-          pk = (unsigned long long)z0 | ((unsigned long long)(z1 - z0) << 8);
-          for (int z = z0; z < z1; ++z) pk |= (unsigned long long)p.nbr[m].col[z] << (12 + 5 * (z - z0));
+        if (!p.coef[m]) continue;
+        const NbrTable& nb = p.nbr[m];
+        unsigned long long a = 0, b = 0;
+        int base = 0;                                   // first slab row of neighbour index k
+        for (int k = 0; k < TC_MAXDEG; ++k) {
+          int rank = 0;                                 // joints before j that have a neighbour k
+          for (int j = 0; j < J; ++j) {
+            const int z0 = nb.row_ptr[j], dg = nb.row_ptr[j + 1] - z0;
+            if (k >= dg) continue;
+            int sp = -1;                                // position of the joint itself in its CSR row
+            for (int z = 0; z < dg; ++z) if (nb.col[z0 + z] == j) sp = z;
+            const int idx = (sp < 0) ? k : (k == 0 ? sp : (k - 1 < sp ? k - 1 : k));
+            const int z = z0 + idx, row = base + rank;
+            if (j == ji) {
+              if (k == 0) a |= (unsigned long long)dg | ((unsigned long long)(sp >= 0 ? 1 : 0) << 4);
+              a |= (unsigned long long)nb.col[z] << (5 + 5 * k);
+              b |= (unsigned long long)row << (6 * k);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (row == ((et + 128 * u) >> 3)) lz = (lz & ~(0xffull << (8 * (4 * m + u)))) | ((unsigned long long)z << (8 * (4 * m + u)));
+            ++rank;
+          }
+          base += rank;
         }
-        if (m == 0) nbr_pk0 = pk; else nbr_pk1 = pk;
+        if (m == 0) { sA0 = a; sB0 = b; } else { sA1 = a; sB1 = b; }
       }
     }
     for (int tile = cid; tile < total_tiles; tile += ncl) {
@@ -1119,16 +1147,18 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         // (all loads first, then the stores: nnz <= TC_MAX_NNZ = 64 rows x 8 float4 = at most 4 per thread;
         //  load->store pairs one after the other exposed one global latency each, ~2000 cycles per tile)
         float4 cfv[TC_MAX_NNZ * 8 / 128];
+        static_assert(TC_MAX_NNZ * 8 / 128 == 4, "lz holds 4 slots per mask");
 #pragma unroll
         for (int u = 0; u < TC_MAX_NNZ * 8 / 128; ++u) {
-          const int i = et + 128 * u, z = i >> 3, g = (i & 7) * 4;
+          const int i = et + 128 * u, g = (i & 7) * 4;
+          const int z = (int)((lz >> (8 * (4 * mask_ + u))) & 0xff);       // CSR nonzero of slab row i / 8
           cfv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (i < nnz_ * 8 && c0_ + g < p.C) cfv[u] = ldg4(p.coef[mask_] + (long long)z * p.C + c0_ + g);
+          if (z != 0xff && c0_ + g < p.C) cfv[u] = ldg4(p.coef[mask_] + (long long)z * p.C + c0_ + g);
         }
 #pragma unroll
         for (int u = 0; u < TC_MAX_NNZ * 8 / 128; ++u) {
-          const int i = et + 128 * u, z = i >> 3, g = (i & 7) * 4;
-          if (i < nnz_ * 8) *reinterpret_cast<float4*>(coef_w + z * TC_SLD + g) = cfv[u];
+          const int i = et + 128 * u, g = (i & 7) * 4;
+          if (i < nnz_ * 8) *reinterpret_cast<float4*>(coef_w + (i >> 3) * TC_SLD + g) = cfv[u];
         }
       }
       float* ab_g = eh ? (scratch + 2 * 128 * TC_XLD) : ab_s;   // per-group copy of the a/b tile
@@ -1289,8 +1319,9 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           // this row's neighbour list comes packed in a register (built once per kernel): the loop is
           // fully unrolled and predicated, so the shared-memory loads of all neighbours can be in flight
           // together (a runtime z loop with an indexed constant load per step exposed ~2 latencies per neighbour)
-          const unsigned long long pk = mask ? nbr_pk1 : nbr_pk0;
-          const int z0 = (int)(pk & 0xff), cnt = valid ? (int)((pk >> 8) & 0xf) : 0;
+          const unsigned long long ta_ = mask ? sA1 : sA0, tb_ = mask ? sB1 : sB0;
+          const int cnt = valid ? (int)(ta_ & 0xf) : 0;
+          const bool self0 = ((ta_ >> 4) & 1) != 0;
 #pragma unroll
           for (int gq = 0; gq < 2; ++gq) {           // 16 channels at a time
             float o[16];
@@ -1304,17 +1335,24 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
 #pragma unroll
             for (int k = 0; k < TC_MAXDEG; ++k) {
               if (k < cnt) {
-                const int jn = (int)((pk >> (12 + 5 * k)) & 31);
-                const float* hrow = Hs + (fb + jn) * TC_XLD + gq * 16;
-                const float* crow = coef_r + (z0 + k) * TC_SLD + gq * 16;
-                const bool self = (jn == ji);
+                const int jn = (int)((ta_ >> (5 + 5 * k)) & 31);
+                const float* crow = coef_r + (int)((tb_ >> (6 * k)) & 63) * TC_SLD + gq * 16;
+                if (k == 0 && self0) {                 // the joint itself: X.W0 of this row, from registers
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  float4 cf = *reinterpret_cast<const float4*>(crow + g * 4);
-                  float4 hv = *reinterpret_cast<const float4*>(hrow + g * 4);
-                  if (self) hv = make_float4(h0[gq * 16 + g * 4], h0[gq * 16 + g * 4 + 1], h0[gq * 16 + g * 4 + 2], h0[gq * 16 + g * 4 + 3]);
-                  o[g * 4] = fmaf(cf.x, hv.x, o[g * 4]); o[g * 4 + 1] = fmaf(cf.y, hv.y, o[g * 4 + 1]);
-                  o[g * 4 + 2] = fmaf(cf.z, hv.z, o[g * 4 + 2]); o[g * 4 + 3] = fmaf(cf.w, hv.w, o[g * 4 + 3]);
+                  for (int g = 0; g < 4; ++g) {
+                    const float4 cf = *reinterpret_cast<const float4*>(crow + g * 4);
+                    o[g * 4] = fmaf(cf.x, h0[gq * 16 + g * 4], o[g * 4]); o[g * 4 + 1] = fmaf(cf.y, h0[gq * 16 + g * 4 + 1], o[g * 4 + 1]);
+                    o[g * 4 + 2] = fmaf(cf.z, h0[gq * 16 + g * 4 + 2], o[g * 4 + 2]); o[g * 4 + 3] = fmaf(cf.w, h0[gq * 16 + g * 4 + 3], o[g * 4 + 3]);
+                  }
+                } else {
+                  const float* hrow = Hs + (fb + jn) * TC_XLD + gq * 16;
+#pragma unroll
+                  for (int g = 0; g < 4; ++g) {
+                    const float4 cf = *reinterpret_cast<const float4*>(crow + g * 4);
+                    const float4 hv = *reinterpret_cast<const float4*>(hrow + g * 4);
+                    o[g * 4] = fmaf(cf.x, hv.x, o[g * 4]); o[g * 4 + 1] = fmaf(cf.y, hv.y, o[g * 4 + 1]);
+                    o[g * 4 + 2] = fmaf(cf.z, hv.z, o[g * 4 + 2]); o[g * 4 + 3] = fmaf(cf.w, hv.w, o[g * 4 + 3]);
+                  }
                 }
               }
             }
