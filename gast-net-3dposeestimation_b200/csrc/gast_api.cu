@@ -17,6 +17,7 @@
 #include "gemm_ffma.cuh"
 #include "kernels_misc.cuh"
 #include "gemm_tc.cuh"
+#include "kernels_hbm.cuh"
 #include "train_kernels.cuh"
 #include "train_state.cuh"
 
@@ -107,6 +108,7 @@ struct gast_handle {
   size_t ev_used = 0;
   int fpt = 0;
   int sm_count = 148;
+  float* loss_scratch = nullptr;   // shrink+mpjpe: SHL_MAXBLOCKS double partials | ticket (zero-initialised, reset by the kernel)
 };
 
 constexpr int GAST_MAX_PENDING_TRAIN = 16;   // training forwards that may wait for their backward per handle
@@ -260,6 +262,7 @@ extern "C" int gast_create(gast_t** out, const gast_cfg* cfg) {
       nd *= fw;
     }
     rc |= dalloc(h, &h->We, (size_t)C * cfg->filter_widths[0] * cfg->in_features) | dalloc(h, &h->be, C);
+    rc |= dalloc(h, &h->loss_scratch, 2 * 1024 + 4);   // shrink+mpjpe partials and ticket (SHL_MAXBLOCKS doubles + 1 word)
   } else {
     h->blocks.resize(1);
     const int C = cfg->channels;
@@ -614,13 +617,42 @@ static int launch_gemm(gast_handle* h, cudaStream_t st, int epi, const GemmP& p,
   return 0;
 }
 
+// resident blocks per SM of a persistent kernel (= its grid per SM), asked once per kernel / shape / device
+static int persistent_bps(const void* fn, int threads, size_t smem, int device) {
+  static std::unordered_map<unsigned long long, int> occ;
+  const unsigned long long key = ((unsigned long long)(uintptr_t)fn * 0x9E3779B97F4A7C15ull) ^ ((unsigned long long)(device & 63) << 58) ^
+                                 ((unsigned long long)threads << 40) ^ (unsigned long long)smem;
+  auto it = occ.find(key);
+  if (it != occ.end()) return it->second;
+  int bps = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, threads, smem) != cudaSuccess) bps = 0;
+  occ[key] = bps;
+  return bps;
+}
+
 static int launch_rowdot(gast_handle* h, cudaStream_t st, const float* X, int ldx, const BlockConsts& b,
                          float* ab, long long rows) {
   if (rows <= 0) return 0;
   const int Q = 2 * b.heads;
   unsigned blocks = cdiv(rows * 32, 256);
   TimedLaunch tl(h, st, LK_ROWDOT);
-  if (Q == 8 && b.C % 4 == 0 && (size_t)8 * b.C * sizeof(float) <= 48 * 1024) {
+  // streaming form (kernels_hbm.cuh): rows arrive by bulk copy into a shared-memory ring of a persistent block
+  static const bool rd_stream = !(getenv("GAST_ROWDOT_STREAM") && atoi(getenv("GAST_ROWDOT_STREAM")) == 0);
+  const int rd_nst = (rowdot_stream_smem(b.C, RDS_STAGES) <= 60 * 1024) ? RDS_STAGES : 2;
+  if (rd_stream && Q == 8 && ldx == b.C && b.C % 128 == 0 && rowdot_chunk_bytes(b.C) % (4 * b.C) == 0 && ((uintptr_t)X % 16) == 0 &&
+      rowdot_stream_smem(b.C, rd_nst) <= 112 * 1024) {
+    static bool attr_rd[64];                               // the shared-memory opt-in is per device
+    if (!attr_rd[h->cfg.device & 63]) {
+      CUDA_OK(cudaFuncSetAttribute(rowdot8_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+      attr_rd[h->cfg.device & 63] = true;
+    }
+    const size_t ssm = rowdot_stream_smem(b.C, rd_nst);
+    const int cb = rowdot_chunk_bytes(b.C);
+    const long long nchunks = (rows * 4 * b.C + cb - 1) / cb;
+    const int bps = std::max(1, persistent_bps((const void*)rowdot8_stream_kernel, RDS_THREADS, ssm, h->cfg.device));
+    const unsigned g = (unsigned)std::min<long long>((nchunks + RDS_WARPS - 1) / RDS_WARPS, (long long)h->sm_count * bps);
+    rowdot8_stream_kernel<<<g, RDS_THREADS, ssm, st>>>(X, b.U, b.cab, ab, rows, b.C, cb, rd_nst);
+  } else if (Q == 8 && b.C % 4 == 0 && (size_t)8 * b.C * sizeof(float) <= 48 * 1024) {
     unsigned g = (unsigned)std::min<long long>((rows * 32 + 255) / 256, (long long)h->sm_count * 8);
     rowdot8_kernel<<<g, 256, sizeof(float) * 8 * b.C, st>>>(X, ldx, b.U, b.cab, ab, rows, b.C);
   } else if (Q == 8) rowdot_kernel<8><<<blocks, 256, 0, st>>>(X, ldx, b.U, b.cab, ab, rows, b.C);
@@ -678,7 +710,69 @@ static int run_global(gast_handle* h, cudaStream_t st, BlockConsts& b, const flo
     int fpb = GV >= nthr ? 1 : nthr / GV;
     fpb = std::max(1, std::min(fpb, (int)(40 * 1024 / (sizeof(float) * b.heads * J * MIX_JP))));   // attention rows fit 40 KB
     const size_t smem = sizeof(float) * (size_t)fpb * b.heads * J * MIX_JP;
-    {
+    // tiled / streaming forms (kernels_hbm.cuh): persistent blocks, the g and a/b slabs of a frame group arrive by bulk copy.
+    // GAST_MIX_MODE: 2 = tiled (g stays in shared memory, default), 1 = register-resident stream kernel, 0 = global_mix_kernel
+    static const int mix_mode = getenv("GAST_MIX_MODE") ? atoi(getenv("GAST_MIX_MODE")) : 2;
+    static const int mix_stages = getenv("GAST_MIX_STAGES") ? std::max(1, std::min(atoi(getenv("GAST_MIX_STAGES")), 3)) : 3;
+    const bool bulk_ok = Ng % 4 == 0 && (J * 2 * b.heads) % 4 == 0 && ((uintptr_t)out_G % 16) == 0 && ((uintptr_t)w.AB % 16) == 0 &&
+                         ((uintptr_t)w.Y % 16) == 0;
+    const int sfpb = (Ng / 4 <= MIXS_THREADS && MIXS_THREADS % (Ng / 4) == 0) ? MIXS_THREADS / (Ng / 4) : 0;
+    bool launched = false;
+    if (mix_mode == 2 && bulk_ok) {
+      const int GV = Ng / 4;
+      const int IW = (((J + 2) / 3) * 3 < ((J + 3) / 4) * 4) ? 3 : 4;        // fewer idle output slots (17 joints: 3)
+      const int per_frame = mixt_nig(J, IW) * GV;
+      const int tfpb = std::max(1, MIXT_MAXTHREADS / per_frame);
+      const int total = tfpb * per_frame;
+      const int passes = (total + MIXT_MAXTHREADS - 1) / MIXT_MAXTHREADS;
+      const int nt = (((total + passes - 1) / passes) + 31) / 32 * 32;
+      int stg = mix_stages;
+      while (stg > 1 && mix_tile_smem(tfpb, J, b.heads, Ng, IW, stg) > 100 * 1024) --stg;
+      const size_t ssm = mix_tile_smem(tfpb, J, b.heads, Ng, IW, stg);
+      if (ssm <= 112 * 1024) {
+        const void* fn = IW == 3 ? (stg == 3 ? (const void*)global_mix_tile_kernel<3, 3> : stg == 2 ? (const void*)global_mix_tile_kernel<3, 2>
+                                                                                                     : (const void*)global_mix_tile_kernel<3, 1>)
+                                 : (stg == 3 ? (const void*)global_mix_tile_kernel<4, 3> : stg == 2 ? (const void*)global_mix_tile_kernel<4, 2>
+                                                                                                     : (const void*)global_mix_tile_kernel<4, 1>);
+        static bool attr_t[64][2][4];
+        bool& done = attr_t[h->cfg.device & 63][IW - 3][stg];
+        if (!done) { CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024)); done = true; }
+        const int bps = persistent_bps(fn, nt, ssm, h->cfg.device);
+        if (bps >= 1) {
+          const long long ngroups = cdiv(F, tfpb);
+          const unsigned grid = (unsigned)std::min<long long>(ngroups, (long long)h->sm_count * bps);
+          const float* a_G = out_G; const float* a_ab = w.AB; const float* a_ck = b.Ck; float* a_Y = w.Y;
+          long long a_F = F; int a_J = J, a_h = b.heads, a_Cg = b.Cg, a_fpb = tfpb;
+          void* args[] = {&a_G, &a_ab, &a_ck, &a_Y, &a_F, &a_J, &a_h, &a_Cg, &a_fpb};
+          TimedLaunch tl(h, st, LK_GLOBAL_MIX);
+          CUDA_OK(cudaLaunchKernel(fn, dim3(grid), dim3(nt), args, ssm, st));
+          h->launches++;
+          launched = true;
+        }
+      }
+    }
+    if (!launched && mix_mode == 1 && bulk_ok && sfpb > 0 && mix_stream_smem(sfpb, J, b.heads, Ng, mix_stages) <= 140 * 1024) {
+      const int sst = mix_stages;
+      const size_t ssm = mix_stream_smem(sfpb, J, b.heads, Ng, sst);
+      static bool attr_mix[64][4];                         // the shared-memory opt-in is per device
+      bool& done = attr_mix[h->cfg.device & 63][sst];
+      if (!done) {
+        const void* fn = sst == 1 ? (const void*)global_mix_stream_kernel<1> : sst == 2 ? (const void*)global_mix_stream_kernel<2>
+                                                                                          : (const void*)global_mix_stream_kernel<3>;
+        CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
+        done = true;
+      }
+      const long long ngroups = cdiv(F, sfpb);
+      const int per_sm = std::max(1, (int)((220 * 1024) / (ssm + 1024)));
+      const unsigned grid = (unsigned)std::min<long long>(ngroups, (long long)h->sm_count * per_sm);
+      TimedLaunch tl(h, st, LK_GLOBAL_MIX);
+      if (sst == 1) global_mix_stream_kernel<1><<<grid, MIXS_THREADS, ssm, st>>>(out_G, w.AB, b.Ck, w.Y, F, J, b.heads, b.Cg, sfpb);
+      else if (sst == 2) global_mix_stream_kernel<2><<<grid, MIXS_THREADS, ssm, st>>>(out_G, w.AB, b.Ck, w.Y, F, J, b.heads, b.Cg, sfpb);
+      else global_mix_stream_kernel<3><<<grid, MIXS_THREADS, ssm, st>>>(out_G, w.AB, b.Ck, w.Y, F, J, b.heads, b.Cg, sfpb);
+      h->launches++;
+      launched = true;
+    }
+    if (!launched) {
       TimedLaunch tl(h, st, LK_GLOBAL_MIX);
       if (vn == 2)
         global_mix_kernel<float2, 2 * MIX_THREADS><<<cdiv(F, fpb), 2 * MIX_THREADS, smem, st>>>(out_G, Ng, w.AB, b.Ck, w.Y, Ng, F, J, b.heads, b.Cg, fpb);
@@ -769,8 +863,27 @@ extern "C" size_t gast_workspace_bytes(const gast_t* h, int32_t B, int32_t T, in
   return a.off + 256;
 }
 
+static int forward_impl(gast_t* h, const float* x, float* y, int32_t B, int32_t T, int32_t strided_now,
+                        void* workspace, size_t workspace_bytes, void* stream, const float* target, float* loss);
+
 extern "C" int gast_forward(gast_t* h, const float* x, float* y, int32_t B, int32_t T, int32_t strided_now,
                             void* workspace, size_t workspace_bytes, void* stream) {
+  return forward_impl(h, x, y, B, T, strided_now, workspace, workspace_bytes, stream, nullptr, nullptr);
+}
+
+// forward + mpjpe of the prediction against `target` (B, T_out, J, 3) in one call: the caller-side pair
+// `predicted = model(x); error = mpjpe(predicted, target)` of main.py:evaluate / train with the loss taken in the shrink
+// kernel's epilogue
+extern "C" int gast_forward_mpjpe(gast_t* h, const float* x, const float* target, float* y, float* loss, int32_t B, int32_t T,
+                                  int32_t strided_now, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return fail("gast_forward_mpjpe: null handle");
+  if (h->cfg.kind != GAST_KIND_MODEL) return fail("gast_forward_mpjpe: only the MODEL kind has a shrink layer");
+  if (!target || !loss) return fail("gast_forward_mpjpe: target and loss must be device pointers");
+  return forward_impl(h, x, y, B, T, strided_now, workspace, workspace_bytes, stream, target, loss);
+}
+
+static int forward_impl(gast_t* h, const float* x, float* y, int32_t B, int32_t T, int32_t strided_now,
+                        void* workspace, size_t workspace_bytes, void* stream, const float* target, float* loss) {
   if (!h) return fail("gast_forward: null handle");
   if (!h->prepared) return fail("gast_forward: gast_prepare() has not run since the last gast_bind()");
   if (B <= 0 || T <= 0) return fail("gast_forward: empty batch (B=%d T=%d)", B, T);
@@ -821,7 +934,19 @@ extern "C" int gast_forward(gast_t* h, const float* x, float* y, int32_t B, int3
     const float* xs = x + (long long)b0 * T * J * c.in_features;
     float* a0 = mb.act[0] + (long long)b0 * g.T0 * J * C;
     float* a1 = mb.act[1] + (long long)b0 * g.T0 * J * 2 * C;
-    {
+    static const bool expand_staged = !(getenv("GAST_EXPAND_STAGED") && atoi(getenv("GAST_EXPAND_STAGED")) == 0);
+    if (expand_staged && expand_rows_ok(C)) {
+      // staged form (kernels_hbm.cuh): inputs of 128 rows gathered once into shared memory, weights in registers
+      TimedLaunch tl(h, st, LK_EXPAND);
+      const unsigned nblk = (unsigned)cdiv(rows, EXS_ROWS);
+      if (c.filter_widths[0] * c.in_features <= 6)
+        expand_rows_kernel<6><<<nblk, EXS_THREADS, 0, st>>>(xs, h->We, h->be, a0, rows, J, T, g.T0, g.s0,
+                                                            c.filter_widths[0], c.in_features, C);
+      else
+        expand_rows_kernel<EXP_MAXKF><<<nblk, EXS_THREADS, 0, st>>>(xs, h->We, h->be, a0, rows, J, T, g.T0, g.s0,
+                                                                    c.filter_widths[0], c.in_features, C);
+      h->launches++;
+    } else {
       long long thr = ((rows + EXP_ROWS - 1) / EXP_ROWS) * (C / 4);
       TimedLaunch tl(h, st, LK_EXPAND);
       if (c.filter_widths[0] * c.in_features <= 6)
@@ -871,9 +996,20 @@ extern "C" int gast_forward(gast_t* h, const float* x, float* y, int32_t B, int3
     const float* ws = Lk.get("shrink.weight", (int64_t)3 * Cl);
     if (!Lk.ok) return 1;
     long long rows = F * J;
+    if (target) {
+      static_assert(SHL_MAXBLOCKS == 1024, "loss_scratch is sized for 1024 block partials");
+      if (!h->loss_scratch) return fail("gast_forward_mpjpe: handle has no loss scratch");
+      double* partial = reinterpret_cast<double*>(h->loss_scratch);
+      unsigned* ticket = reinterpret_cast<unsigned*>(h->loss_scratch + 2 * SHL_MAXBLOCKS);
+      const unsigned nb = (unsigned)std::min<long long>(SHL_MAXBLOCKS, (rows + 7) / 8);
+      TimedLaunch tl(h, st, LK_SHRINK);
+      shrink_mpjpe_kernel<<<nb, 256, 0, st>>>(mb.act[cur], Cl, ws, y, rows, Cl, target, partial, ticket, loss);
+      h->launches++;
+    } else {
     TimedLaunch tl(h, st, LK_SHRINK);
     shrink_kernel<<<cdiv(rows * 32, 256), 256, 0, st>>>(mb.act[cur], Cl, ws, y, rows, Cl);
     h->launches++;
+    }
   }
   CUDA_OK(cudaGetLastError());
   return 0;

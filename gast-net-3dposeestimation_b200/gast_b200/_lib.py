@@ -15,7 +15,7 @@ KIND_MODEL, KIND_BLOCK, KIND_LOCAL, KIND_MGLOBAL, KIND_SEMCH, KIND_GLOBAL_HEAD =
 
 # every symbol include/gast_b200.h declares
 SYMBOLS = ['gast_create', 'gast_destroy', 'gast_bind', 'gast_prepare', 'gast_out_frames',
-           'gast_receptive_field', 'gast_workspace_bytes', 'gast_forward',
+           'gast_receptive_field', 'gast_workspace_bytes', 'gast_forward', 'gast_forward_mpjpe',
            'gast_last_launch_count', 'gast_last_tc_launch_count', 'gast_set_timing',
            'gast_get_timings', 'gast_set_gemm_core', 'gast_debug_gemm', 'gast_bind_grads',
            'gast_train_workspace_bytes', 'gast_forward_train', 'gast_backward', 'gast_set_dropout_state', 'gast_tta_prepare', 'gast_tta_merge',
@@ -69,6 +69,8 @@ def load():
     lib.gast_workspace_bytes.restype = C.c_size_t
     lib.gast_forward.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, C.c_size_t, vp]
     lib.gast_forward.restype = C.c_int
+    lib.gast_forward_mpjpe.argtypes = [vp, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, C.c_size_t, vp]
+    lib.gast_forward_mpjpe.restype = C.c_int
     lib.gast_last_launch_count.argtypes = [vp]
     lib.gast_last_launch_count.restype = C.c_int32
     lib.gast_last_tc_launch_count.argtypes = [vp]

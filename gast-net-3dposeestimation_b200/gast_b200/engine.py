@@ -184,6 +184,18 @@ class _Handle(object):
                                      strided_now, C.c_void_p(self.ws.data_ptr()), self.ws.numel(),
                                      C.c_void_p(stream)), 'gast_forward')
 
+    def forward_mpjpe(self, x, target, y, loss, B, T, strided_now, stream):
+        need = self.lib.gast_workspace_bytes(self.h, B, T, strided_now)
+        if need == 0:
+            raise GastError('gast_workspace_bytes: %s' % L.last_error())
+        if self.ws is None or self.ws.numel() < need:
+            self.ws = None
+            self.ws = torch.empty(int(need), dtype=torch.uint8, device=self.device)
+        _check(self.lib.gast_forward_mpjpe(self.h, C.c_void_p(x.data_ptr()), C.c_void_p(target.data_ptr()),
+                                           C.c_void_p(y.data_ptr()), C.c_void_p(loss.data_ptr()), B, T, strided_now,
+                                           C.c_void_p(self.ws.data_ptr()), self.ws.numel(), C.c_void_p(stream)),
+               'gast_forward_mpjpe')
+
     def launches(self):
         return int(self.lib.gast_last_launch_count(self.h))
 
@@ -341,6 +353,37 @@ def run_model(module, x):
         h.forward(x, y, B, T, strided_now, st)
     module.__dict__['_gast_last_launches'] = h.launches()
     return y
+
+
+def run_model_mpjpe(module, x, target):
+    """`predicted = model(x); error = mpjpe(predicted, target)` (main.py:270-300, common/loss.py:5-11) as ONE library
+    call: the loss is taken in the shrink kernel's epilogue.  Eval mode; returns (predicted, loss) with loss a 0-d
+    CUDA tensor.  (The training loss goes through gast_b200.pipeline.mpjpe, which also produces the gradient.)"""
+    _require_cuda(x, 'run_model_mpjpe')
+    _require_cuda(target, 'run_model_mpjpe (target)')
+    _no_train(module, 'run_model_mpjpe')
+    dev = x.device
+    h = model_handle(module, dev)
+    x = x.contiguous()
+    B, T = int(x.shape[0]), int(x.shape[1])
+    strided_now = 1 if (module._gast_strided or
+                        (T == module.receptive_field() and not module._gast_dense)) else 0
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        h.refresh(module, st)
+        T_out = h.lib.gast_out_frames(h.h, T, strided_now)
+        if T_out <= 0:
+            raise GastError('forward: %s' % L.last_error())
+        shape = (B, T_out, module.num_joints_in, 3)
+        if tuple(target.shape) != shape or target.device != dev:
+            raise GastError('run_model_mpjpe: target must be %s on %s (got %s on %s)'
+                            % (shape, dev, tuple(target.shape), target.device))
+        target = target.contiguous()
+        y = torch.empty(shape, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        h.forward_mpjpe(x, target, y, loss, B, T, strided_now, st)
+    module.__dict__['_gast_last_launches'] = h.launches()
+    return y, loss
 
 
 def run_block(module, x):

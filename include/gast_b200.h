@@ -99,6 +99,14 @@ size_t gast_workspace_bytes(const gast_t* h, int32_t B, int32_t T, int32_t strid
 int gast_forward(gast_t* h, const float* x, float* y, int32_t B, int32_t T,
                  int32_t strided_now, void* workspace, size_t workspace_bytes, void* stream);
 
+/* forward + mpjpe in one call: the caller-side pair `predicted = model(x); error = mpjpe(predicted, target)` of
+ * main.py:evaluate (main.py:270-300) and of the training loop's validation pass, with the loss of common/loss.py:5-11
+ * taken in the shrink kernel's epilogue (no second pass over the prediction).  MODEL kind only.
+ *   target (B,T_out,J,3) fp32 device; y as gast_forward; *loss (device float) = mean over B*T_out*J joints of
+ *   ||y - target||_2.  Block partial sums are double and are added in a fixed order: the loss is reproducible run to run. */
+int gast_forward_mpjpe(gast_t* h, const float* x, const float* target, float* y, float* loss, int32_t B, int32_t T,
+                       int32_t strided_now, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Number of kernels the last gast_forward enqueued (for bench.py's gpu_launches). */
 int32_t gast_last_launch_count(const gast_t* h);
 
