@@ -18,11 +18,6 @@
 #include "kernels_misc.cuh"
 #include "gemm_tc.cuh"
 #include "kernels_hbm.cuh"
-// default of the streaming row-dot / tiled attention-mix kernels of kernels_hbm.cuh when GAST_ROWDOT_STREAM / GAST_MIX_MODE are
-// not set (0 until the full GPU suite has passed with them; the staged expand kernel has)
-#ifndef GAST_HBM_DEFAULTS
-#define GAST_HBM_DEFAULTS 0
-#endif
 #include "train_kernels.cuh"
 #include "train_state.cuh"
 
@@ -622,42 +617,13 @@ static int launch_gemm(gast_handle* h, cudaStream_t st, int epi, const GemmP& p,
   return 0;
 }
 
-// resident blocks per SM of a persistent kernel (= its grid per SM), asked once per kernel / shape / device
-static int persistent_bps(const void* fn, int threads, size_t smem, int device) {
-  static std::unordered_map<unsigned long long, int> occ;
-  const unsigned long long key = ((unsigned long long)(uintptr_t)fn * 0x9E3779B97F4A7C15ull) ^ ((unsigned long long)(device & 63) << 58) ^
-                                 ((unsigned long long)threads << 40) ^ (unsigned long long)smem;
-  auto it = occ.find(key);
-  if (it != occ.end()) return it->second;
-  int bps = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, threads, smem) != cudaSuccess) bps = 0;
-  occ[key] = bps;
-  return bps;
-}
-
 static int launch_rowdot(gast_handle* h, cudaStream_t st, const float* X, int ldx, const BlockConsts& b,
                          float* ab, long long rows) {
   if (rows <= 0) return 0;
   const int Q = 2 * b.heads;
   unsigned blocks = cdiv(rows * 32, 256);
   TimedLaunch tl(h, st, LK_ROWDOT);
-  // streaming form (kernels_hbm.cuh): rows arrive by bulk copy into a shared-memory ring of a persistent block
-  static const bool rd_stream = getenv("GAST_ROWDOT_STREAM") ? atoi(getenv("GAST_ROWDOT_STREAM")) != 0 : (GAST_HBM_DEFAULTS != 0);
-  const int rd_nst = (rowdot_stream_smem(b.C, RDS_STAGES) <= 60 * 1024) ? RDS_STAGES : 2;
-  if (rd_stream && Q == 8 && ldx == b.C && b.C % 128 == 0 && rowdot_chunk_bytes(b.C) % (4 * b.C) == 0 && ((uintptr_t)X % 16) == 0 &&
-      rowdot_stream_smem(b.C, rd_nst) <= 112 * 1024) {
-    static bool attr_rd[64];                               // the shared-memory opt-in is per device
-    if (!attr_rd[h->cfg.device & 63]) {
-      CUDA_OK(cudaFuncSetAttribute(rowdot8_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-      attr_rd[h->cfg.device & 63] = true;
-    }
-    const size_t ssm = rowdot_stream_smem(b.C, rd_nst);
-    const int cb = rowdot_chunk_bytes(b.C);
-    const long long nchunks = (rows * 4 * b.C + cb - 1) / cb;
-    const int bps = std::max(1, persistent_bps((const void*)rowdot8_stream_kernel, RDS_THREADS, ssm, h->cfg.device));
-    const unsigned g = (unsigned)std::min<long long>((nchunks + RDS_WARPS - 1) / RDS_WARPS, (long long)h->sm_count * bps);
-    rowdot8_stream_kernel<<<g, RDS_THREADS, ssm, st>>>(X, b.U, b.cab, ab, rows, b.C, cb, rd_nst);
-  } else if (Q == 8 && b.C % 4 == 0 && (size_t)8 * b.C * sizeof(float) <= 48 * 1024) {
+  if (Q == 8 && b.C % 4 == 0 && (size_t)8 * b.C * sizeof(float) <= 48 * 1024) {
     unsigned g = (unsigned)std::min<long long>((rows * 32 + 255) / 256, (long long)h->sm_count * 8);
     rowdot8_kernel<<<g, 256, sizeof(float) * 8 * b.C, st>>>(X, ldx, b.U, b.cab, ab, rows, b.C);
   } else if (Q == 8) rowdot_kernel<8><<<blocks, 256, 0, st>>>(X, ldx, b.U, b.cab, ab, rows, b.C);
@@ -715,69 +681,7 @@ static int run_global(gast_handle* h, cudaStream_t st, BlockConsts& b, const flo
     int fpb = GV >= nthr ? 1 : nthr / GV;
     fpb = std::max(1, std::min(fpb, (int)(40 * 1024 / (sizeof(float) * b.heads * J * MIX_JP))));   // attention rows fit 40 KB
     const size_t smem = sizeof(float) * (size_t)fpb * b.heads * J * MIX_JP;
-    // tiled / streaming forms (kernels_hbm.cuh): persistent blocks, the g and a/b slabs of a frame group arrive by bulk copy.
-    // GAST_MIX_MODE: 2 = tiled (g stays in shared memory, default), 1 = register-resident stream kernel, 0 = global_mix_kernel
-    static const int mix_mode = getenv("GAST_MIX_MODE") ? atoi(getenv("GAST_MIX_MODE")) : (GAST_HBM_DEFAULTS ? 2 : 0);
-    static const int mix_stages = getenv("GAST_MIX_STAGES") ? std::max(1, std::min(atoi(getenv("GAST_MIX_STAGES")), 3)) : 3;
-    const bool bulk_ok = Ng % 4 == 0 && (J * 2 * b.heads) % 4 == 0 && ((uintptr_t)out_G % 16) == 0 && ((uintptr_t)w.AB % 16) == 0 &&
-                         ((uintptr_t)w.Y % 16) == 0;
-    const int sfpb = (Ng / 4 <= MIXS_THREADS && MIXS_THREADS % (Ng / 4) == 0) ? MIXS_THREADS / (Ng / 4) : 0;
-    bool launched = false;
-    if (mix_mode == 2 && bulk_ok) {
-      const int GV = Ng / 4;
-      const int IW = (((J + 2) / 3) * 3 < ((J + 3) / 4) * 4) ? 3 : 4;        // fewer idle output slots (17 joints: 3)
-      const int per_frame = mixt_nig(J, IW) * GV;
-      const int tfpb = std::max(1, MIXT_MAXTHREADS / per_frame);
-      const int total = tfpb * per_frame;
-      const int passes = (total + MIXT_MAXTHREADS - 1) / MIXT_MAXTHREADS;
-      const int nt = (((total + passes - 1) / passes) + 31) / 32 * 32;
-      int stg = mix_stages;
-      while (stg > 1 && mix_tile_smem(tfpb, J, b.heads, Ng, IW, stg) > 100 * 1024) --stg;
-      const size_t ssm = mix_tile_smem(tfpb, J, b.heads, Ng, IW, stg);
-      if (ssm <= 112 * 1024) {
-        const void* fn = IW == 3 ? (stg == 3 ? (const void*)global_mix_tile_kernel<3, 3> : stg == 2 ? (const void*)global_mix_tile_kernel<3, 2>
-                                                                                                     : (const void*)global_mix_tile_kernel<3, 1>)
-                                 : (stg == 3 ? (const void*)global_mix_tile_kernel<4, 3> : stg == 2 ? (const void*)global_mix_tile_kernel<4, 2>
-                                                                                                     : (const void*)global_mix_tile_kernel<4, 1>);
-        static bool attr_t[64][2][4];
-        bool& done = attr_t[h->cfg.device & 63][IW - 3][stg];
-        if (!done) { CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024)); done = true; }
-        const int bps = persistent_bps(fn, nt, ssm, h->cfg.device);
-        if (bps >= 1) {
-          const long long ngroups = cdiv(F, tfpb);
-          const unsigned grid = (unsigned)std::min<long long>(ngroups, (long long)h->sm_count * bps);
-          const float* a_G = out_G; const float* a_ab = w.AB; const float* a_ck = b.Ck; float* a_Y = w.Y;
-          long long a_F = F; int a_J = J, a_h = b.heads, a_Cg = b.Cg, a_fpb = tfpb;
-          void* args[] = {&a_G, &a_ab, &a_ck, &a_Y, &a_F, &a_J, &a_h, &a_Cg, &a_fpb};
-          TimedLaunch tl(h, st, LK_GLOBAL_MIX);
-          CUDA_OK(cudaLaunchKernel(fn, dim3(grid), dim3(nt), args, ssm, st));
-          h->launches++;
-          launched = true;
-        }
-      }
-    }
-    if (!launched && mix_mode == 1 && bulk_ok && sfpb > 0 && mix_stream_smem(sfpb, J, b.heads, Ng, mix_stages) <= 140 * 1024) {
-      const int sst = mix_stages;
-      const size_t ssm = mix_stream_smem(sfpb, J, b.heads, Ng, sst);
-      static bool attr_mix[64][4];                         // the shared-memory opt-in is per device
-      bool& done = attr_mix[h->cfg.device & 63][sst];
-      if (!done) {
-        const void* fn = sst == 1 ? (const void*)global_mix_stream_kernel<1> : sst == 2 ? (const void*)global_mix_stream_kernel<2>
-                                                                                          : (const void*)global_mix_stream_kernel<3>;
-        CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
-        done = true;
-      }
-      const long long ngroups = cdiv(F, sfpb);
-      const int per_sm = std::max(1, (int)((220 * 1024) / (ssm + 1024)));
-      const unsigned grid = (unsigned)std::min<long long>(ngroups, (long long)h->sm_count * per_sm);
-      TimedLaunch tl(h, st, LK_GLOBAL_MIX);
-      if (sst == 1) global_mix_stream_kernel<1><<<grid, MIXS_THREADS, ssm, st>>>(out_G, w.AB, b.Ck, w.Y, F, J, b.heads, b.Cg, sfpb);
-      else if (sst == 2) global_mix_stream_kernel<2><<<grid, MIXS_THREADS, ssm, st>>>(out_G, w.AB, b.Ck, w.Y, F, J, b.heads, b.Cg, sfpb);
-      else global_mix_stream_kernel<3><<<grid, MIXS_THREADS, ssm, st>>>(out_G, w.AB, b.Ck, w.Y, F, J, b.heads, b.Cg, sfpb);
-      h->launches++;
-      launched = true;
-    }
-    if (!launched) {
+    {
       TimedLaunch tl(h, st, LK_GLOBAL_MIX);
       if (vn == 2)
         global_mix_kernel<float2, 2 * MIX_THREADS><<<cdiv(F, fpb), 2 * MIX_THREADS, smem, st>>>(out_G, Ng, w.AB, b.Ck, w.Y, Ng, F, J, b.heads, b.Cg, fpb);
