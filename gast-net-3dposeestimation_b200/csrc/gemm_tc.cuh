@@ -394,6 +394,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// SemCH neighbour mix with packed fp32x2 FMAs (fma.rn.f32x2): o[0..3] += cf * hv element by element, each half rounded
+// like the scalar FFMA (bit-identical), half the FMA issue slots of the epilogue warps
+#ifndef GAST_TC_SEMCH_FFMA2
+#define GAST_TC_SEMCH_FFMA2 1
+#endif
+__device__ __forceinline__ void semch_fma2(const float4 cf, const float4 hv, float* o) {
+  const float2 lo = __ffma2_rn(make_float2(cf.x, cf.y), make_float2(hv.x, hv.y), make_float2(o[0], o[1]));
+  const float2 hi = __ffma2_rn(make_float2(cf.z, cf.w), make_float2(hv.z, hv.w), make_float2(o[2], o[3]));
+  o[0] = lo.x; o[1] = lo.y; o[2] = hi.x; o[3] = hi.y;
+}
+
 // named barrier of one epilogue warpgroup (128 threads): id 1 = columns 0-63, id 2 = columns 64-127
 __device__ __forceinline__ void epi_bar_sync(uint32_t id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
@@ -1223,6 +1234,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           tmem_ld32_async(taddr + 32, vb);
           tmem_wait_ld(va);
           tmem_wait_ld(vb);
+          // (packed add.rn.f32x2 here made ptxas spill in the PLAIN kernel: the pair alignment fights the tcgen05.ld targets)
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             acc[i] += __uint_as_float(va[i]);
@@ -1341,8 +1353,13 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
 #pragma unroll
                   for (int g = 0; g < 4; ++g) {
                     const float4 cf = *reinterpret_cast<const float4*>(crow + g * 4);
+#if GAST_TC_SEMCH_FFMA2
+                    semch_fma2(cf, make_float4(h0[gq * 16 + g * 4], h0[gq * 16 + g * 4 + 1], h0[gq * 16 + g * 4 + 2],
+                                               h0[gq * 16 + g * 4 + 3]), o + g * 4);
+#else
                     o[g * 4] = fmaf(cf.x, h0[gq * 16 + g * 4], o[g * 4]); o[g * 4 + 1] = fmaf(cf.y, h0[gq * 16 + g * 4 + 1], o[g * 4 + 1]);
                     o[g * 4 + 2] = fmaf(cf.z, h0[gq * 16 + g * 4 + 2], o[g * 4 + 2]); o[g * 4 + 3] = fmaf(cf.w, h0[gq * 16 + g * 4 + 3], o[g * 4 + 3]);
+#endif
                   }
                 } else {
                   const float* hrow = Hs + (fb + jn) * TC_XLD + gq * 16;
@@ -1350,8 +1367,12 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
                   for (int g = 0; g < 4; ++g) {
                     const float4 cf = *reinterpret_cast<const float4*>(crow + g * 4);
                     const float4 hv = *reinterpret_cast<const float4*>(hrow + g * 4);
+#if GAST_TC_SEMCH_FFMA2
+                    semch_fma2(cf, hv, o + g * 4);
+#else
                     o[g * 4] = fmaf(cf.x, hv.x, o[g * 4]); o[g * 4 + 1] = fmaf(cf.y, hv.y, o[g * 4 + 1]);
                     o[g * 4 + 2] = fmaf(cf.z, hv.z, o[g * 4 + 2]); o[g * 4 + 3] = fmaf(cf.w, hv.w, o[g * 4 + 3]);
+#endif
                   }
                 }
               }
