@@ -210,6 +210,8 @@ def test_error_behaviour():
         m(torch.zeros(2, 20, 17, 2, device='cuda'))      # shorter than the receptive field
     with pytest.raises(RuntimeError):
         m(torch.zeros(2, 27, 17, 2))                     # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(0, 27, 17, 2, device='cuda'))      # empty batch: the reference raises too (view(0, C, -1) of 0 elements, global_attention.py:56)
     with pytest.raises(KeyError):
         LocalGraph(torch.eye(14), 16, 16)                # local_attention.py:89-90
     with pytest.raises(AssertionError):
