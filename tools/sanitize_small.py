@@ -2,7 +2,6 @@
 forward+mpjpe call, one training step and one pushed frame of a causal stream, each checked against the other path."""
 import os
 import sys
-import numpy as np
 import torch
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
