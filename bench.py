@@ -472,8 +472,9 @@ def main():
     from gast_b200 import _lib
     ver = _lib.load().gast_version().decode()
     # bf16-equivalent tensor passes per MAC: TF32 runs at half the bf16 rate, so 3xTF32 costs 6; one TF32 product
-    # + two bf16 correction products cost 2 + 2 = 4
-    div = 4 if 'bf16-corr' in ver else 6
+    # + two bf16 correction products cost 2 + 2 = 4; three fp16 products (hi.hi + lo.hi + hi.lo) cost 3 (the K < 256
+    # layers of block 1, ~10 % of the FLOPs, stay on the 4-pass form: the bound is quoted for the 3-pass one)
+    div = 3 if 'fp16 hi+lo' in ver else 4 if 'bf16-corr' in ver else 6
     roof['arithmetic'] = ver
     roof['frac_of_fp32_parity_bound'] = roof['frac'] * div
     roof['note'] = ('fp32-grade arithmetic (parity bar 1e-4 abs): every MAC costs %d bf16-equivalent tensor passes, so the '

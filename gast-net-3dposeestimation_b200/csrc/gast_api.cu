@@ -44,7 +44,11 @@ static int fail(const char* fmt, ...) {
   } while (0)
 
 extern "C" const char* gast_last_error(void) { return g_err; }
-extern "C" const char* gast_version(void) { return "gast_b200 0.2 (sm_100a; tcgen05 tf32 + bf16-corr)"; }
+extern "C" const char* gast_version(void) {
+  static const bool f16 = !(getenv("GAST_TC_F16") && atoi(getenv("GAST_TC_F16")) == 0);
+  return f16 ? "gast_b200 0.3 (sm_100a; tcgen05 fp16 hi+lo for K >= 256, tf32 + bf16-corr below)"
+             : "gast_b200 0.3 (sm_100a; tcgen05 tf32 + bf16-corr)";
+}
 
 // ------------------------------------------------------------------------------------------
 // handle
@@ -932,7 +936,11 @@ static int prep_one_tc(gast_handle* h, cudaStream_t st, TcWeights& t, const floa
 // ------------------------------------------------------------------------------------------
 static int prep_one_tc(gast_handle* h, cudaStream_t st, TcWeights& t, const float* W, int N, int K, int semch) {
   if (!W) return 0;
-  int rc = tc_prepare_weights(t, W, N, K, st, &h->owned, semch);
+  // inference arithmetic of the tcgen05 core: 2 = every operand fp16 (hi and remainder: 22 significant bits, 3 bf16-rate
+  // products per MAC; GEMMs with K >= 256 whose weights fit fp16's range, see tc_prepare_weights), 0 = tf32 + bf16
+  // corrections (4 bf16-equivalent products per MAC, fp32's range).  GAST_TC_F16=0 selects the latter everywhere.
+  static const int inf_prec = (getenv("GAST_TC_F16") && atoi(getenv("GAST_TC_F16")) == 0) ? 0 : 2;
+  int rc = tc_prepare_weights(t, W, N, K, st, &h->owned, semch, inf_prec);
   if (rc) return fail("tcgen05 weight preparation failed (%d): %s", rc,
                       rc > 0 ? cudaGetErrorString((cudaError_t)rc) : "cuTensorMapEncodeTiled unavailable/failed");
   return 0;
@@ -1105,8 +1113,8 @@ extern "C" int gast_debug_gemm(const float* A, const float* W, float* out, int32
   std::vector<void*> owned;
   TcWeights t;
   int sms = 148;
-  const int prec = (core == 2) ? 1 : 0;     // core 2 = the tcgen05 core in 3xTF32 arithmetic (training)
-  if (core == 2) core = 0;
+  const int prec = (core == 2) ? 1 : (core == 3) ? 2 : 0;     // core 2 = the tcgen05 core in 3xTF32 arithmetic (training); 3 = fp16 hi
+  if (core == 2 || core == 3) core = 0;
   if (core == 0) {
     int dev = 0;
     cudaGetDevice(&dev);

@@ -41,6 +41,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <string.h>
 #include <vector>
 #include "gast_common.cuh"
@@ -320,6 +321,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_k, float hi_k) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_k), "f"(lo_k));
   return d;
 }
+// two fp32 -> packed fp16 pair (lower k in the low half), round to nearest, SATURATING at +-65504 (no inf operand), and
+// the pair back as two fp32 (exact)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo_k, float hi_k) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_k), "f"(lo_k));
+  return d;
+}
+__device__ __forceinline__ void unpack_f16x2(uint32_t d, float& lo_k, float& hi_k) {
+  asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(lo_k), "=f"(hi_k) : "r"(d));
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -434,6 +445,13 @@ constexpr uint32_t TC_IDESC2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(
                                ((uint32_t)((2 * TC_BM) >> 4) << 24);
 constexpr uint32_t TC_IDESC2_BF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
                                   ((uint32_t)((2 * TC_BM) >> 4) << 24);
+// PREC = 2 (CTA pair): every operand fp16 (kind::f16 format code 0).  (Mixed formats -- a bf16 remainder against an fp16
+// hi operand -- raise "illegal instruction": A and B of one kind::f16 MMA must have the same type, GPU session Z4.)
+constexpr uint32_t TC_IDESC2_HH = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+// weights are split as 2^TC_F16_WSHIFT * W (their remainder then sits in fp16's normal range: |W| ~ 0.03 has a remainder of
+// ~1e-5, below fp16's smallest normal 6.1e-5); the epilogue multiplies the group sums by 2^-TC_F16_WSHIFT (exact)
+constexpr int TC_F16_WSHIFT = 8;
+constexpr float TC_F16_WSCALE = 256.f, TC_F16_WUNSCALE = 1.f / 256.f;
 // the same with A=B=bf16 (kind::f16 format code 1), for the correction products
 constexpr uint32_t TC_IDESC_BF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
                                  ((uint32_t)(TC_BM >> 4) << 24);
@@ -676,6 +694,16 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         // (splitting by TRUNCATION -- the raw value as the tf32 operand, x - trunc(x) as the correction -- saves an
         //  integer op per element but measured no faster and doubles the error of the bf16 correction:
         //  profiles/r02_tc_attribution.md, experiment 11)
+        if (PREC == 2) {
+          // fp16 hi (11 significant bits, like tf32) | fp16 remainder: 32 pair columns [h16(k = 0..31) | lo(k = 0..31)]
+          const uint32_t p01 = pack_f16x2_sat(x.x, x.y), p23 = pack_f16x2_sat(x.z, x.w);
+          float g0, g1, g2, g3;
+          unpack_f16x2(p01, g0, g1); unpack_f16x2(p23, g2, g3);
+          lo[2 * i + 0] = p01; lo[2 * i + 1] = p23;
+          lo[16 + 2 * i + 0] = pack_f16x2_sat(x.x - g0, x.y - g1);
+          lo[16 + 2 * i + 1] = pack_f16x2_sat(x.z - g2, x.w - g3);
+          continue;
+        }
         const float h0 = tf32_rn_fast(x.x), h1 = tf32_rn_fast(x.y), h2 = tf32_rn_fast(x.z), h3 = tf32_rn_fast(x.w);
         hi[4 * i + 0] = __float_as_uint(h0); hi[4 * i + 1] = __float_as_uint(h1);
         hi[4 * i + 2] = __float_as_uint(h2); hi[4 * i + 3] = __float_as_uint(h3);
@@ -723,7 +751,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         mbar_wait(bar0 + BA_EMPTY + 8 * stage, phase ^ 1);
         tc_fence_after();
         const uint32_t ta = tmem_base + lane_off + TC_A_COL + stage * 64;
-        tmem_st32(ta, hi);
+        if (PREC != 2) tmem_st32(ta, hi);      // (PREC 2: no fp32 operand -- the stage is its 32 pair columns)
         tmem_st32(ta + 32, lo);
 #if GAST_TC_CONV_ST_EARLY
         // the tensor-memory stores are in flight: request the next chunk's rows in their shadow (only if they have
@@ -771,6 +799,15 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (DBG != 9) x = *reinterpret_cast<const float4*>(rowp + ((i ^ sw) << 2));
         if (atma && !row_in_box) x = make_float4(0.f, 0.f, 0.f, 0.f);   // rows the box does not cover
+        if (PREC == 2) {
+          const uint32_t p01 = pack_f16x2_sat(x.x, x.y), p23 = pack_f16x2_sat(x.z, x.w);
+          float g0, g1, g2, g3;
+          unpack_f16x2(p01, g0, g1); unpack_f16x2(p23, g2, g3);
+          lo[2 * i + 0] = p01; lo[2 * i + 1] = p23;
+          lo[16 + 2 * i + 0] = pack_f16x2_sat(x.x - g0, x.y - g1);
+          lo[16 + 2 * i + 1] = pack_f16x2_sat(x.z - g2, x.w - g3);
+          continue;
+        }
         const float h0 = tf32_rn_fast(x.x), h1 = tf32_rn_fast(x.y), h2 = tf32_rn_fast(x.z), h3 = tf32_rn_fast(x.w);
         hi[4 * i + 0] = __float_as_uint(h0); hi[4 * i + 1] = __float_as_uint(h1);
         hi[4 * i + 2] = __float_as_uint(h2); hi[4 * i + 3] = __float_as_uint(h3);
@@ -800,7 +837,7 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
       tc_fence_after();
       const uint32_t ta = tmem_base + lane_off + TC_A_COL + stage * 64;
       if (DBG != 4 && DBG != 5 && DBG != 8 && DBG != 9) {
-        tmem_st32(ta, hi);
+        if (PREC != 2) tmem_st32(ta, hi);
         tmem_st32(ta + 32, lo);
         tmem_wait_st();
       }
@@ -847,9 +884,10 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           if (CG == 2) {
             // CTA pair: this CTA's 64 weight rows (hi and pk) into ITS shared memory; the bytes of both CTAs are counted
             // on the rank-0 CTA's barrier, which its issuer waits on
-            if (crank == 0) mbar_arrive_expect_tx(full, 2 * 16384);
+            if (crank == 0) mbar_arrive_expect_tx(full, (PREC == 2 ? 1 : 2) * 16384);
             const uint32_t dst = sbase + stage * BSB;
             const uint32_t lfull = lead_bar0 + BB_FULL + 8 * (2 * stage + gof.role());
+            if (PREC != 2)   // (PREC 2: the [h16 | lo] rows are the only B operand: 8 KB per CTA and chunk)
             tma_load_2d_cg2(dst, &map_hi, lfull, c * TC_BK, n0 + (TC_BN / 2) * (int)crank);
             tma_load_2d_cg2(dst + BPK, &map_lo, lfull, (PREC == 1 ? 1 : 2) * c * TC_BK, n0 + (TC_BN / 2) * (int)crank);
             if (++stage == BST) { stage = 0; phase ^= 1; }
@@ -1024,6 +1062,16 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           // the loop body took ~700 with one elected block per k-step: profiles/r02_tc_attribution.md).  The probes
           // of the next chunk's barriers follow in the shadow of the MMAs just queued.
           if (elect_one()) {
+            if (PREC == 2) {
+              // 6 MMAs of K = 16 on 16-bit operands (tensor-pipe time of 3 bf16 passes instead of 4): per 16-wide k-step
+              //   A_h16.B_h16 + A_lo.B_h16 + A_h16.B_lo ; pair columns [h16 (16) | lo (16)], B row [h16 (64 B) | lo (64 B)]
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                umma_bf16_ts2(d_main, a_pk + 8 * k, b_pk + (uint64_t)(2 * k), TC_IDESC2_HH, (cg | k) ? 1u : 0u);
+                umma_bf16_ts2(d_main, a_pk + 16 + 8 * k, b_pk + (uint64_t)(2 * k), TC_IDESC2_HH, 1u);
+                umma_bf16_ts2(d_main, a_pk + 8 * k, b_pk + (uint64_t)(2 * (k + 2)), TC_IDESC2_HH, 1u);
+              }
+            } else
 #pragma unroll
             for (int k = 0; k < TC_BK / 8; ++k) {
               const uint64_t adv = (uint64_t)(k * 2);      // 8 fp32 = 32 B = 2 x 16 B
@@ -1210,6 +1258,10 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           tmem_ld32_async(taddr + 32, au + 32);
           tmem_wait_ld(au);
           tmem_wait_ld(au + 32);
+          if (PREC == 2) {                     // weights were split as 2^8 W
+#pragma unroll
+            for (int i = 0; i < TC_EN; ++i) acc[i] *= TC_F16_WUNSCALE;
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -1237,8 +1289,13 @@ gemm_tc_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensor
           // (packed add.rn.f32x2 here made ptxas spill in the PLAIN kernel: the pair alignment fights the tcgen05.ld targets)
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
+            if (PREC == 2) {                   // exact power-of-two scale folded into the round-to-nearest add
+              acc[i] = fmaf(__uint_as_float(va[i]), TC_F16_WUNSCALE, acc[i]);
+              acc[32 + i] = fmaf(__uint_as_float(vb[i]), TC_F16_WUNSCALE, acc[32 + i]);
+            } else {
             acc[i] += __uint_as_float(va[i]);
             acc[32 + i] += __uint_as_float(vb[i]);
+            }
           }
         }
         tc_fence_before();
@@ -1552,6 +1609,21 @@ __global__ void tc_split_kernel(const float* __restrict__ w, float* __restrict__
   // order main(k-step 0), correction(0), main(1), correction(1), ...; every one of them truncates the accumulator
   // (prec 1, 3xTF32: 12 MMAs per chunk in the order main(k), A_lo.B_hi(k), A_hi.B_lo(k))
   const int per_k = prec == 1 ? 3 : 2;
+  if (prec == 2) {
+    // fp16 hi | fp16 remainder of 2^8 W, one 128-byte row per chunk as in prec 0; 6 MMAs per chunk in the order
+    // (A_h16.B_h16, A_lo.B_h16, A_h16.B_lo) per 16-wide k-step
+    const float xs = x * TC_F16_WSCALE;            // (tc_prepare_weights checked max|W| * 2^8 < 65504)
+    const __half hh = __float2half_rn(xs);
+    const float hf = __half2float(hh);
+    const int s2 = (c - g * TC_FLUSH) * 6 + 3 * ((k % TC_BK) / 16);
+    const float left = (float)(glen * 6 - s2);
+    const float lo2 = (xs - hf) + TC_TRUNC_C * left * hf;
+    unsigned short* prow2 = pk + row * 2 * K + (long long)c * 2 * TC_BK + (k - c * TC_BK);
+    prow2[0] = __half_as_ushort(hh);
+    prow2[TC_BK] = __half_as_ushort(__float2half_rn(lo2));
+    hi[i] = hf;
+    return;
+  }
   const int s = (c - g * TC_FLUSH) * (per_k * TC_BK / 8) + per_k * ((k % TC_BK) / 8);
   const float steps_left = (float)(glen * (per_k * TC_BK / 8) - s);      // truncations this product still sees
   hi[i] = h;
@@ -1583,10 +1655,42 @@ inline tc_encode_fn tc_get_encode() {
 
 // W: [N][K] fp32 K-major (device).  Allocates hi/lo once, splits, encodes the TMA maps.
 // Returns 0 on success, a cudaError_t / -1 otherwise.
+__global__ void tc_absmax_kernel(const float* __restrict__ w, long long n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float a = fabsf(w[i]);
+    m = (a > m || a != a) ? (a != a ? __int_as_float(0x7f800000) : a) : m;     // NaN counts as "too large"
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));             // non-negative floats order like their bits
+}
+
 inline int tc_prepare_weights(TcWeights& t, const float* W, int N, int K, cudaStream_t st,
                               std::vector<void*>* owned, int semch = 0, int prec = 0) {
   t.ready = false;
   if (K % TC_BK != 0 || N % 4 != 0) return 0;            // shape not taken by this core (FFMA runs it)
+  if (prec == 2 && K < 256) prec = 0;   // K = 128 layers are bound by HBM / their epilogue: nothing to gain, keep fp32's range
+  if (prec == 2) {
+    // the fp16 form needs 2^8 |W| inside fp16's range: a GEMM whose (BatchNorm-folded) weights exceed it keeps tf32 + bf16
+    // (the check reads max|W| back: when the caller is capturing a CUDA graph it cannot, and the GEMM keeps tf32 + bf16)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) prec = 0;
+  }
+  if (prec == 2) {
+    static unsigned* d_max_dev[64] = {};                  // one word per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    unsigned*& d_max = d_max_dev[dev & 63];
+    if (!d_max && cudaMalloc(&d_max, sizeof(unsigned)) != cudaSuccess) return -1;
+    unsigned hmax = 0;
+    cudaMemsetAsync(d_max, 0, sizeof(unsigned), st);
+    tc_absmax_kernel<<<64, 256, 0, st>>>(W, (long long)N * K, d_max);
+    if (cudaMemcpyAsync(&hmax, d_max, sizeof(unsigned), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    float fmax_;
+    memcpy(&fmax_, &hmax, sizeof(float));
+    if (!(fmax_ * TC_F16_WSCALE < 60000.f)) prec = 0;
+  }
   tc_encode_fn enc = tc_get_encode();
   if (!enc) return -1;
   if (!t.hi || t.N != N || t.K != K || t.prec != prec) {
@@ -1735,6 +1839,12 @@ inline int tc_launch(int sm_count, cudaStream_t st, int epi, const GemmP& p, con
     return tc_launch_one<EPI_PLAIN, 0, 1>(grid, st, p, t, nt, (int)items);
   }
 #if GAST_TC_CLUSTER == 2 && !GAST_TC_DUAL_ISSUE
+  if (t.prec == 2) {                       // fp16 hi + bf16 remainder (GAST_TC_F16=1): CTA pair only
+    if (cg != 2 || dbg) return (int)cudaErrorInvalidValue;
+    if (epi == EPI_PLAIN) return tc_launch_one<EPI_PLAIN, 0, 2, 2>(grid, st, p, t, nt, (int)items);
+    if (epi == EPI_SEMCH) return tc_launch_one<EPI_SEMCH, 0, 2, 2>(grid, st, p, t, nt, (int)items);
+    return tc_launch_one<EPI_GLOBAL, 0, 2, 2>(grid, st, p, t, nt, (int)items);
+  }
   if (cg == 2 && !dbg) {
     if (epi == EPI_PLAIN) return tc_launch_one<EPI_PLAIN, 0, 0, 2>(grid, st, p, t, nt, (int)items);
     if (epi == EPI_SEMCH) return tc_launch_one<EPI_SEMCH, 0, 0, 2>(grid, st, p, t, nt, (int)items);

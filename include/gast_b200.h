@@ -218,7 +218,7 @@ int gast_adam_step(const int64_t* table, int32_t n_chunks, float* exp_avg, float
                    double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step, void* stream);
 
 /* Test/probe entry (not on the forward path): out[M,N] = A[M,K] . W[N,K]^T on one GEMM core
- * (core 0 = tcgen05 TF32 + bf16 corrections [inference], 1 = FFMA, 2 = tcgen05 3xTF32 [training]).  tc_mode != 0 selects a timing-experiment variant of the
+ * (core 0 = tcgen05 TF32 + bf16 corrections, 1 = FFMA, 2 = tcgen05 3xTF32 [training], 3 = tcgen05 fp16 hi + remainder [inference, K >= 256]).  tc_mode != 0 selects a timing-experiment variant of the
  * tcgen05 kernel (parts disabled; results invalid).  Runs once, then `reps` timed launches
  * (CUDA events) whose mean duration is written to *ms_out (host).  Synchronises the stream. */
 int gast_debug_gemm(const float* A, const float* W, float* out, int32_t M, int32_t N, int32_t K,

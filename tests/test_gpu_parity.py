@@ -132,6 +132,30 @@ def test_against_oracle_random_shapes(core):
         assert np.abs(y - ref).max() < tol, (J, fw, ch, B, T, np.abs(y - ref).max())
 
 
+def test_fp16_form_falls_back_for_weights_outside_fp16_range():
+    """GEMMs with K >= 256 run on fp16 operands (hi and remainder of 2^8 W, csrc/gemm_tc.cuh PREC = 2; activations above
+    65504 would saturate -- GAST_TC_F16=0 selects tf32 + bf16 corrections, fp32's range, everywhere).  A weight matrix
+    that does not fit fp16's range must keep the tf32 form on its own (tc_prepare_weights reads max|W| back): checked on
+    one GEMM through gast_debug_gemm (core 3 = request the fp16 form) against fp64."""
+    import ctypes as C
+    from gast_b200 import _lib
+    lib = _lib.load()
+    rs = np.random.RandomState(3)
+    M, N, K = 384, 128, 512
+    A = rs.standard_normal((M, K)).astype(np.float32)
+    for wscale, bar in ((1.0 / np.sqrt(K), 2e-6), (300.0, 2e-6)):          # second: 2^8 * max|W| ~ 3e5 > 65504
+        W = (rs.standard_normal((N, K)) * wscale).astype(np.float32)
+        a, w = torch.from_numpy(A).cuda(), torch.from_numpy(W).cuda()
+        o = torch.empty((M, N), dtype=torch.float32, device='cuda')
+        rc = lib.gast_debug_gemm(a.data_ptr(), w.data_ptr(), o.data_ptr(), M, N, K, 3, 0, 0, None,
+                                 torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, _lib.last_error()
+        ref = A.astype(np.float64) @ W.astype(np.float64).T
+        d = o.cpu().numpy().astype(np.float64) - ref
+        rel = np.sqrt((d ** 2).mean()) / np.sqrt((ref ** 2).mean())
+        assert np.isfinite(d).all() and rel < bar, (wscale, rel)
+
+
 def test_full_size_properties():
     """BASELINE config 2 at full size (4096 clips): size-independent properties.
     (a) batch independence: a clip's output does not depend on its batch neighbours (bit-exact);

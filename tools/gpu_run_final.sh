@@ -14,7 +14,7 @@ timeout 300 $NCU --metrics gpu__time_duration.sum -s 200 -c 60 --csv --log-file 
 timeout 600 $NCU --set full --import-source on -k regex:"gemm_tc_kernel|global_mix|expand|rowdot8|shrink" -s 81 -c 27 \
     -o /tmp/${T}_full_cfg2 python tools/launch_times.py 4096 17 128 3,3,3 > $O/${T}_ncu_cfg2.log 2>&1; echo "ncu full rc $?"
 ncu -i /tmp/${T}_full_cfg2.ncu-rep --page raw --csv > $O/${T}_raw_cfg2.csv 2>/dev/null
-for id in 0 3 5; do
+for id in 1 2 26; do
   ncu -i /tmp/${T}_full_cfg2.ncu-rep --page source --csv --print-source cuda,sass --launch-skip $id --launch-count 1 2>/dev/null | gzip > $O/${T}_src_$id.csv.gz
 done
 ls -la $O | grep ${T}; du -sh $O

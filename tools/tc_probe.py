@@ -145,7 +145,45 @@ def cg_perf():
         print(line, flush=True)
 
 
+def f16_probe():
+    """fp16-hi arithmetic (gast_debug_gemm core 3: A_h16.B_h16 + A_lo.B_h16 + A_h16.B_lo, kind::f16 MMAs on fp16 operands, weights as 2^8 W)
+    next to tf32 + bf16 corrections (core 0; the remainders are fp16 too: mixed fp16 / bf16 operands of one MMA are illegal) and the FFMA core: error against fp64 and time on the path's GEMM shapes"""
+    rs = np.random.RandomState(0)
+
+    def stats(name, o, ref):
+        d = o.astype(np.float64) - ref
+        sc = np.sqrt((ref ** 2).mean())
+        print('%-52s rel rms %.2e  max %.2e  bias %.2e' % (name, np.sqrt((d ** 2).mean()) / sc, np.abs(d).max() / sc, d.mean() / sc),
+              flush=True)
+    for K in (128, 384, 1536):
+        for kind in ('randsign', 'positive', 'relu_x_small_w'):
+            A = rs.standard_normal((256, K)).astype(np.float32)
+            W = (rs.standard_normal((128, K)) / np.sqrt(K)).astype(np.float32)
+            if kind == 'positive':
+                A, W = np.abs(A), np.abs(W)
+            if kind == 'relu_x_small_w':
+                A, W = np.maximum(A, 0) * 30, W * 1e-3
+            ref = A.astype(np.float64) @ W.astype(np.float64).T
+            for core, name in ((1, 'FFMA fp32'), (0, 'tcgen05 tf32 + bf16 corr'), (3, 'tcgen05 fp16 hi + fp16 lo')):
+                stats('K=%4d %-14s %s' % (K, kind, name), gemm(A, W, core, 0), ref)
+    rs = np.random.RandomState(1)
+    for (M, N, K) in ((75008, 1024, 1536), (224768, 512, 768), (674176, 128, 128), (626688, 256, 384)):
+        a = torch.from_numpy(rs.standard_normal((M, K)).astype(np.float32)).cuda()
+        w = torch.from_numpy(rs.standard_normal((N, K)).astype(np.float32)).cuda()
+        o = torch.empty((M, N), dtype=torch.float32, device='cuda')
+        line = 'M=%d N=%d K=%d |' % (M, N, K)
+        for core, name in ((0, 'tf32+bf16'), (3, 'fp16hi')):
+            ms = C.c_float(0)
+            rc = lib.gast_debug_gemm(a.data_ptr(), w.data_ptr(), o.data_ptr(), M, N, K, core, 0, 5, C.byref(ms),
+                                     torch.cuda.current_stream().cuda_stream)
+            line += ' %s %.4f ms (%.0f TF/s)' % (name, ms.value, 2e-9 * M * N * K / max(ms.value, 1e-6)) if rc == 0 else ' %s ERR(%s)' % (name, _lib.last_error()[:60])
+        print(line, flush=True)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == '--f16':
+        f16_probe()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == '--cg':
         cg_perf()
     elif len(sys.argv) > 1 and sys.argv[1] == '--train':
