@@ -9,7 +9,7 @@ import sys
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(REPO, 'gast-net-3dposeestimation_b200', 'csrc', 'libgast_b200.so')
-full_for = sys.argv[2] if len(sys.argv) > 2 else 'gemm_tc_kernelILi0ELi0ELi0ELi2E'
+full_for = sys.argv[2] if len(sys.argv) > 2 else 'gemm_tc_kernelILi0ELi0ELi2ELi2E'
 sass = subprocess.run(['cuobjdump', '-sass', lib], capture_output=True, text=True).stdout
 demangle = lambda n: subprocess.run(['c++filt', n], capture_output=True, text=True).stdout.strip()
 KEY = ['UTCHMMA', 'UTCQMMA', 'UTCBAR', 'UTCATOMSWS', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UBLKCP', 'SYNCS', 'FFMA2', 'FADD2', 'HMMA', 'MUFU',
